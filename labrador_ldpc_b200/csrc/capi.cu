@@ -1,0 +1,312 @@
+// C ABI of the library: the reference's 21 entry points (single codeword =
+// batch of one on the GPU) plus the batched / stream-ordered additions.
+// Declarations and reference citations: include/labrador_ldpc.h.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/labrador_ldpc.h"
+#include "host_api.h"
+
+using namespace ldpc;
+
+namespace {
+
+const CodeInfo *info(int code) { return code_info(code); }
+
+// 0 host, 1 device, -1 mixed.  Null pointers are skipped.
+int common_kind(std::initializer_list<const void *> ptrs, int *device) {
+    int kind = -2, dev = -1;
+    for (const void *p : ptrs) {
+        if (!p) continue;
+        int d = -1;
+        const int k = classify_pointer(p, &d);
+        if (kind == -2) { kind = k; dev = d; }
+        else if (kind != k || (k == 1 && d != dev)) return -1;
+    }
+    if (device) *device = dev;
+    return kind == -2 ? 0 : kind;
+}
+
+int decode_ms_impl(int code, int ty, const void *llrs, uint8_t *output, size_t batch, size_t max_iters,
+                   uint8_t *success, uint32_t *iters, bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (ty < 0 || ty >= kNumLlrTypes) return fail(LDPC_ERR_BAD_ARGUMENT, "bad llr_type");
+    if (batch == 0) return LDPC_OK;
+    if (!llrs || !output) return fail(LDPC_ERR_NULL_POINTER, "llrs/output must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({llrs, output, success, iters}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_decode_ms(ctx, code, ty, llrs, output, batch, max_iters, success, iters, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({llrs, nullptr, (size_t)c->n * llr_size(ty)});
+    arrays.push_back({nullptr, output, c->output_len()});
+    const int si = success ? (int)arrays.size() : -1;
+    if (success) arrays.push_back({nullptr, success, 1});
+    const int ii = iters ? (int)arrays.size() : -1;
+    if (iters) arrays.push_back({nullptr, iters, 4});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_decode_ms(ctx, code, ty, d[0], static_cast<uint8_t *>(d[1]), nf, max_iters,
+                                si >= 0 ? static_cast<uint8_t *>(d[si]) : nullptr,
+                                ii >= 0 ? static_cast<uint32_t *>(d[ii]) : nullptr, st);
+    });
+}
+
+int decode_bf_impl(int code, const uint8_t *input, uint8_t *output, size_t batch, size_t max_iters,
+                   uint8_t *success, uint32_t *iters, bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (batch == 0) return LDPC_OK;
+    if (!input || !output) return fail(LDPC_ERR_NULL_POINTER, "input/output must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({input, output, success, iters}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_decode_bf(ctx, code, input, output, batch, max_iters, success, iters, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({input, nullptr, (size_t)c->n / 8});
+    arrays.push_back({nullptr, output, c->output_len()});
+    const int si = success ? (int)arrays.size() : -1;
+    if (success) arrays.push_back({nullptr, success, 1});
+    const int ii = iters ? (int)arrays.size() : -1;
+    if (iters) arrays.push_back({nullptr, iters, 4});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_decode_bf(ctx, code, static_cast<const uint8_t *>(d[0]), static_cast<uint8_t *>(d[1]), nf,
+                                max_iters, si >= 0 ? static_cast<uint8_t *>(d[si]) : nullptr,
+                                ii >= 0 ? static_cast<uint32_t *>(d[ii]) : nullptr, st);
+    });
+}
+
+// data == nullptr: encode in place (first k/8 bytes of every codeword already set).
+int encode_impl(int code, const uint8_t *data, uint8_t *codewords, size_t batch, bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (batch == 0) return LDPC_OK;
+    if (!codewords) return fail(LDPC_ERR_NULL_POINTER, "codewords must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({data, codewords}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_encode(ctx, code, data, codewords, batch, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    if (data && data != codewords) {
+        arrays.push_back({data, nullptr, (size_t)c->k / 8});
+        arrays.push_back({nullptr, codewords, (size_t)c->n / 8});
+        return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+            return launch_encode(ctx, code, static_cast<const uint8_t *>(d[0]), static_cast<uint8_t *>(d[1]), nf, st);
+        });
+    }
+    arrays.push_back({codewords, codewords, (size_t)c->n / 8});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_encode(ctx, code, nullptr, static_cast<uint8_t *>(d[0]), nf, st);
+    });
+}
+
+int h2l_impl(int code, int ty, const uint8_t *input, void *llrs, size_t batch, bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (ty < 0 || ty >= kNumLlrTypes) return fail(LDPC_ERR_BAD_ARGUMENT, "bad llr_type");
+    if (batch == 0) return LDPC_OK;
+    if (!input || !llrs) return fail(LDPC_ERR_NULL_POINTER, "input/llrs must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({input, llrs}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_hard_to_llrs(ctx, code, ty, input, llrs, batch, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({input, nullptr, (size_t)c->n / 8});
+    arrays.push_back({nullptr, llrs, (size_t)c->n * llr_size(ty)});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_hard_to_llrs(ctx, code, ty, static_cast<const uint8_t *>(d[0]), d[1], nf, st);
+    });
+}
+
+int l2h_impl(int code, int ty, const void *llrs, uint8_t *output, size_t batch, bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (ty < 0 || ty >= kNumLlrTypes) return fail(LDPC_ERR_BAD_ARGUMENT, "bad llr_type");
+    if (batch == 0) return LDPC_OK;
+    if (!llrs || !output) return fail(LDPC_ERR_NULL_POINTER, "llrs/output must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({llrs, output}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_llrs_to_hard(ctx, code, ty, llrs, output, batch, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({llrs, nullptr, (size_t)c->n * llr_size(ty)});
+    arrays.push_back({nullptr, output, (size_t)c->n / 8});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_llrs_to_hard(ctx, code, ty, d[0], static_cast<uint8_t *>(d[1]), nf, st);
+    });
+}
+
+// The reference-signature functions have no error channel: report and abort.
+void die_if(int rc, const char *fn) {
+    if (rc == LDPC_OK) return;
+    fprintf(stderr, "labrador_ldpc (B200): %s failed: %s (code %d); this library has no CPU fallback\n", fn,
+            last_error(), rc);
+    abort();
+}
+
+bool single_ms(int code, int ty, const void *llrs, uint8_t *output, size_t max_iters, size_t *iters_run,
+               const char *fn) {
+    uint8_t ok = 0;
+    uint32_t it = 0;
+    die_if(decode_ms_impl(code, ty, llrs, output, 1, max_iters, &ok, &it, false, nullptr), fn);
+    if (iters_run) *iters_run = it;
+    return ok != 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t labrador_ldpc_code_n(enum labrador_ldpc_code code) { const CodeInfo *c = info(code); return c ? c->n : 0; }
+size_t labrador_ldpc_code_k(enum labrador_ldpc_code code) { const CodeInfo *c = info(code); return c ? c->k : 0; }
+size_t labrador_ldpc_bf_working_len(enum labrador_ldpc_code code) { const CodeInfo *c = info(code); return c ? c->bf_working_len() : 0; }
+size_t labrador_ldpc_ms_working_u8_len(enum labrador_ldpc_code code) { const CodeInfo *c = info(code); return c ? c->ms_working_u8_len() : 0; }
+size_t labrador_ldpc_ms_working_len(enum labrador_ldpc_code code) { const CodeInfo *c = info(code); return c ? c->ms_working_len() : 0; }
+size_t labrador_ldpc_output_len(enum labrador_ldpc_code code) { const CodeInfo *c = info(code); return c ? c->output_len() : 0; }
+
+void labrador_ldpc_encode(enum labrador_ldpc_code code, uint8_t *codeword) {
+    die_if(encode_impl(code, nullptr, codeword, 1, false, nullptr), "labrador_ldpc_encode");
+}
+
+void labrador_ldpc_copy_encode(enum labrador_ldpc_code code, const uint8_t *data, uint8_t *codeword) {
+    die_if(encode_impl(code, data, codeword, 1, false, nullptr), "labrador_ldpc_copy_encode");
+}
+
+bool labrador_ldpc_decode_bf(enum labrador_ldpc_code code, const uint8_t *input, uint8_t *output,
+                             uint8_t *working, size_t max_iters, size_t *iters_run) {
+    (void)working;
+    uint8_t ok = 0;
+    uint32_t it = 0;
+    die_if(decode_bf_impl(code, input, output, 1, max_iters, &ok, &it, false, nullptr), "labrador_ldpc_decode_bf");
+    if (iters_run) *iters_run = it;
+    return ok != 0;
+}
+
+#define LDPC_SINGLE_MS(SUFFIX, T, TY)                                                                       \
+    bool labrador_ldpc_decode_ms_##SUFFIX(enum labrador_ldpc_code code, const T *llrs, uint8_t *output,      \
+                                          T *working, uint8_t *working_u8, size_t max_iters,                 \
+                                          size_t *iters_run) {                                               \
+        (void)working; (void)working_u8;                                                                    \
+        return single_ms(code, TY, llrs, output, max_iters, iters_run, "labrador_ldpc_decode_ms_" #SUFFIX); \
+    }                                                                                                       \
+    int labrador_ldpc_decode_ms_##SUFFIX##_batch(enum labrador_ldpc_code code, const T *llrs, uint8_t *output, \
+                                                 size_t batch, size_t max_iters, uint8_t *success,           \
+                                                 uint32_t *iters_run) {                                      \
+        return decode_ms_impl(code, TY, llrs, output, batch, max_iters, success, iters_run, false, nullptr); \
+    }                                                                                                       \
+    void labrador_ldpc_hard_to_llrs_##SUFFIX(enum labrador_ldpc_code code, const uint8_t *input, T *llrs) {  \
+        die_if(h2l_impl(code, TY, input, llrs, 1, false, nullptr), "labrador_ldpc_hard_to_llrs_" #SUFFIX);   \
+    }                                                                                                       \
+    void labrador_ldpc_llrs_to_hard_##SUFFIX(enum labrador_ldpc_code code, const T *llrs, uint8_t *output) { \
+        die_if(l2h_impl(code, TY, llrs, output, 1, false, nullptr), "labrador_ldpc_llrs_to_hard_" #SUFFIX);  \
+    }                                                                                                       \
+    int labrador_ldpc_hard_to_llrs_##SUFFIX##_batch(enum labrador_ldpc_code code, const uint8_t *input,      \
+                                                    T *llrs, size_t batch) {                                 \
+        return h2l_impl(code, TY, input, llrs, batch, false, nullptr);                                       \
+    }                                                                                                       \
+    int labrador_ldpc_llrs_to_hard_##SUFFIX##_batch(enum labrador_ldpc_code code, const T *llrs,             \
+                                                    uint8_t *output, size_t batch) {                         \
+        return l2h_impl(code, TY, llrs, output, batch, false, nullptr);                                      \
+    }
+
+LDPC_SINGLE_MS(i8, int8_t, kI8)
+LDPC_SINGLE_MS(i16, int16_t, kI16)
+LDPC_SINGLE_MS(i32, int32_t, kI32)
+LDPC_SINGLE_MS(f32, float, kF32)
+LDPC_SINGLE_MS(f64, double, kF64)
+
+int labrador_ldpc_cuda_init(const int *devices, int n_devices) { return runtime_init(devices, n_devices); }
+void labrador_ldpc_cuda_shutdown(void) { runtime_shutdown(); }
+int labrador_ldpc_cuda_device_count(void) { return runtime_device_count(); }
+const char *labrador_ldpc_last_error(void) { return last_error(); }
+const char *labrador_ldpc_version(void) { return "labrador-ldpc-b200 0.1.0 (drop-in for labrador-ldpc 1.2.1 C API, sm_100a)"; }
+
+void *labrador_ldpc_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void labrador_ldpc_free_pinned(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int labrador_ldpc_decode_bf_batch(enum labrador_ldpc_code code, const uint8_t *input, uint8_t *output,
+                                  size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters_run) {
+    return decode_bf_impl(code, input, output, batch, max_iters, success, iters_run, false, nullptr);
+}
+
+int labrador_ldpc_encode_batch(enum labrador_ldpc_code code, uint8_t *codewords, size_t batch) {
+    return encode_impl(code, nullptr, codewords, batch, false, nullptr);
+}
+
+int labrador_ldpc_copy_encode_batch(enum labrador_ldpc_code code, const uint8_t *data, uint8_t *codewords,
+                                    size_t batch) {
+    if (!data && batch) return fail(LDPC_ERR_NULL_POINTER, "data must not be NULL");
+    return encode_impl(code, data, codewords, batch, false, nullptr);
+}
+
+int labrador_ldpc_decode_ms_batch_async(enum labrador_ldpc_code code, int llr_type, const void *llrs,
+                                        uint8_t *output, size_t batch, size_t max_iters, uint8_t *success,
+                                        uint32_t *iters_run, void *cuda_stream) {
+    return decode_ms_impl(code, llr_type, llrs, output, batch, max_iters, success, iters_run, true,
+                          static_cast<cudaStream_t>(cuda_stream));
+}
+
+int labrador_ldpc_decode_bf_batch_async(enum labrador_ldpc_code code, const uint8_t *input, uint8_t *output,
+                                        size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters_run,
+                                        void *cuda_stream) {
+    return decode_bf_impl(code, input, output, batch, max_iters, success, iters_run, true,
+                          static_cast<cudaStream_t>(cuda_stream));
+}
+
+int labrador_ldpc_copy_encode_batch_async(enum labrador_ldpc_code code, const uint8_t *data, uint8_t *codewords,
+                                          size_t batch, void *cuda_stream) {
+    return encode_impl(code, data, codewords, batch, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int labrador_ldpc_hard_to_llrs_batch_async(enum labrador_ldpc_code code, int llr_type, const uint8_t *input,
+                                           void *llrs, size_t batch, void *cuda_stream) {
+    return h2l_impl(code, llr_type, input, llrs, batch, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int labrador_ldpc_llrs_to_hard_batch_async(enum labrador_ldpc_code code, int llr_type, const void *llrs,
+                                           uint8_t *output, size_t batch, void *cuda_stream) {
+    return l2h_impl(code, llr_type, llrs, output, batch, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+unsigned long long labrador_ldpc_kernel_launch_count(void) { return launch_count(); }
+
+const char *labrador_ldpc_decode_ms_kernel_name(enum labrador_ldpc_code code, int llr_type) {
+    if (!info(code)) return "invalid";
+    return decode_ms_kernel_name(code, llr_type);
+}
+
+uint32_t labrador_ldpc_edge_table_crc(enum labrador_ldpc_code code) {
+    const CodeInfo *c = info(code);
+    return c ? edge_crc(*c) : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// One-time host expansion of the compact code descriptions (see code_tables.h).
+#include "code_tables.h"
+
+#include <mutex>
+
+#include "ccsds_tables.h"
+
+namespace ldpc {
+namespace {
+
+struct Raw {
+    const char *name;
+    int n, k, p, m, b, edges;
+    const uint8_t *proto;     // [3][4][11]
+    const uint16_t *phi;      // [4][26] or nullptr (TC codes have no permutation blocks)
+    const uint64_t *gen;
+};
+
+// Literal parameters: reference src/codes/mod.rs:109-241.  phi table per M:
+// src/codes/mod.rs:469-478; prototype per rate: src/codes/mod.rs:480-486.
+const Raw kRaw[kNumCodes] = {
+    {"TC128", 128, 64, 0, 16, 16, 512, ccsds_proto_tc128, nullptr, ccsds_gen_tc128},
+    {"TC256", 256, 128, 0, 32, 32, 1024, ccsds_proto_tc256, nullptr, ccsds_gen_tc256},
+    {"TC512", 512, 256, 0, 64, 64, 2048, ccsds_proto_tc512, nullptr, ccsds_gen_tc512},
+    {"TM1280", 1280, 1024, 128, 128, 32, 4992, ccsds_proto_tm_r45, ccsds_phi_m128, ccsds_gen_tm1280},
+    {"TM1536", 1536, 1024, 256, 256, 64, 5888, ccsds_proto_tm_r23, ccsds_phi_m256, ccsds_gen_tm1536},
+    {"TM2048", 2048, 1024, 512, 512, 128, 7680, ccsds_proto_tm_r12, ccsds_phi_m512, ccsds_gen_tm2048},
+    {"TM5120", 5120, 4096, 512, 512, 128, 19968, ccsds_proto_tm_r45, ccsds_phi_m512, ccsds_gen_tm5120},
+    {"TM6144", 6144, 4096, 1024, 1024, 256, 23552, ccsds_proto_tm_r23, ccsds_phi_m1024, ccsds_gen_tm6144},
+    {"TM8192", 8192, 4096, 2048, 2048, 512, 30720, ccsds_proto_tm_r12, ccsds_phi_m2048, ccsds_gen_tm8192},
+};
+
+CodeInfo g_info[kNumCodes];
+std::once_flag g_once;
+
+// Block enumeration in the reference iterator's order: prototype rows, then
+// columns, then the summed sub-prototypes of a cell until its first zero entry
+// (reference src/codes/mod.rs:295-361).
+void build_all() {
+    for (int ci = 0; ci < kNumCodes; ci++) {
+        const Raw &r = kRaw[ci];
+        CodeInfo &c = g_info[ci];
+        c.name = r.name;
+        c.n = r.n; c.k = r.k; c.p = r.p; c.m = r.m; c.b = r.b;
+        c.edges = r.edges;
+        c.checks = r.n + r.p - r.k;
+        c.vars = r.n + r.p;
+        c.rows = c.checks / c.m;
+        c.cols = c.vars / c.m;
+        c.gen = r.gen;
+        c.n_blocks = 0;
+        int offset = 0;
+        for (int row = 0; row < 4; row++) {
+            for (int col = 0; col < 11; col++) {
+                for (int sub = 0; sub < 3; sub++) {
+                    const uint8_t e = r.proto[(sub * 4 + row) * 11 + col];
+                    if (e == 0) break;
+                    const int kind = e & CCSDS_KIND_MASK;
+                    const int val = e & CCSDS_VAL_MASK;
+                    Block &b = c.blocks[c.n_blocks++];
+                    b.row = row; b.col = col;
+                    b.shift = 0; b.theta = 0;
+                    b.phi[0] = b.phi[1] = b.phi[2] = b.phi[3] = 0;
+                    b.edge_offset = offset;
+                    if (kind == CCSDS_KIND_IDENT) {
+                        b.kind = kIdentity;
+                        b.shift = val % c.m;
+                    } else {
+                        b.kind = kPermutation;
+                        b.theta = ccsds_theta_k[val];
+                        for (int j = 0; j < 4; j++) b.phi[j] = r.phi[j * 26 + val] % (c.m / 4);
+                    }
+                    offset += c.m;
+                }
+            }
+        }
+        // degrees
+        std::vector<int> vd(c.vars, 0), cd(c.checks, 0);
+        std::vector<uint32_t> chk, var;
+        expand_edges(c, chk, var);
+        for (size_t i = 0; i < chk.size(); i++) { vd[var[i]]++; cd[chk[i]]++; }
+        c.max_var_degree = 0; c.max_check_degree = 0;
+        for (int d : vd) if (d > c.max_var_degree) c.max_var_degree = d;
+        for (int d : cd) if (d > c.max_check_degree) c.max_check_degree = d;
+    }
+}
+
+inline int block_pi(const CodeInfo &c, const Block &b, int i) {
+    if (b.kind == kIdentity) return (i + b.shift) % c.m;
+    const int q = c.m / 4;
+    const int j = i / q;
+    return q * ((b.theta + j) % 4) + ((b.phi[j] + i) % q);
+}
+
+}  // namespace
+
+const CodeInfo *code_info(int code) {
+    if (code < 0 || code >= kNumCodes) return nullptr;
+    std::call_once(g_once, build_all);
+    return &g_info[code];
+}
+
+void expand_edges(const CodeInfo &c, std::vector<uint32_t> &check, std::vector<uint32_t> &var) {
+    check.clear(); var.clear();
+    check.reserve(c.edges); var.reserve(c.edges);
+    for (int bi = 0; bi < c.n_blocks; bi++) {
+        const Block &b = c.blocks[bi];
+        for (int i = 0; i < c.m; i++) {
+            check.push_back((uint32_t)(b.row * c.m + i));
+            var.push_back((uint32_t)(b.col * c.m + block_pi(c, b, i)));
+        }
+    }
+}
+
+uint32_t edge_crc(const CodeInfo &c) {
+    std::vector<uint32_t> chk, var;
+    expand_edges(c, chk, var);
+    uint32_t crc = 0xFFFFFFFFu;
+    auto step = [&crc](uint32_t data) {
+        crc ^= data;
+        for (int i = 0; i < 16; i++) crc = (crc >> 1) ^ ((crc & 1) ? 0xEDB88320u : 0u);
+    };
+    for (size_t i = 0; i < chk.size(); i++) { step(chk[i]); step(var[i]); }
+    return crc;
+}
+
+void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::vector<uint32_t> &chk_tab) {
+    std::vector<uint32_t> chk, var;
+    expand_edges(c, chk, var);
+    var_tab.assign((size_t)c.max_var_degree * c.vars, kNoEdge);
+    chk_tab.assign((size_t)c.max_check_degree * c.checks, kNoEdge);
+    std::vector<int> vfill(c.vars, 0), cfill(c.checks, 0);
+    for (uint32_t idx = 0; idx < chk.size(); idx++) {
+        const uint32_t a = var[idx], ch = chk[idx];
+        var_tab[(size_t)vfill[a]++ * c.vars + a] = idx | (ch << 16);
+        chk_tab[(size_t)cfill[ch]++ * c.checks + ch] = idx | (a << 16);
+    }
+}
+
+}  // namespace ldpc

@@ -1,0 +1,68 @@
+// Host-side description of the nine CCSDS codes and the one-time expansion of
+// the compact parity-check prototypes into block descriptors and edge tables.
+//
+// Replaces (as data, built once per process instead of re-derived per edge):
+//   CodeParams / *_PARAMS            reference src/codes/mod.rs:69-241
+//   ParityIter::next + iterator setup reference src/codes/mod.rs:275-362, 444-494
+//   compact_generator()              reference src/codes/mod.rs:412-424
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+namespace ldpc {
+
+constexpr int kNumCodes = 9;
+constexpr int kMaxBlocks = 40;     // r4/5 prototype has 39 non-zero blocks
+constexpr uint32_t kNoEdge = 0xFFFFFFFFu;
+
+enum BlockKind : int { kIdentity = 1, kPermutation = 2 };
+
+// One non-zero MxM block of H.  Edges of the block are i = 0..M-1:
+//   check = row*M + i,  idx = edge_offset + i,
+//   var   = col*M + pi(i)  with
+//   identity:    pi(i) = (i + shift) mod M
+//   permutation: pi(i) = Q*((theta + i/Q) mod 4) + ((phi[i/Q] + i) mod Q),  Q = M/4
+struct Block {
+    int row, col, kind;
+    int shift;          // identity only
+    int theta;          // permutation only
+    int phi[4];         // permutation only
+    int edge_offset;    // idx of the block's first edge in reference order
+};
+
+struct CodeInfo {
+    const char *name;
+    int n, k, p, m, b;
+    int edges;               // paritycheck_sum
+    int checks;              // n + p - k
+    int vars;                // n + p
+    int rows, cols;          // active prototype rows / columns
+    const uint64_t *gen;     // compact generator, (k/b) x ((n-k)/64) words, MSB = parity bit 0
+    int n_blocks;
+    Block blocks[kMaxBlocks];
+    int max_var_degree, max_check_degree;
+
+    // reference src/decoder.rs:93-116
+    size_t bf_working_len() const { return (size_t)n + p; }
+    size_t ms_working_len() const { return 2 * (size_t)edges + 3 * (size_t)n + 3 * (size_t)p - 2 * (size_t)k; }
+    size_t ms_working_u8_len() const { return (size_t)(n + p - k) / 8; }
+    size_t output_len() const { return (size_t)(n + p) / 8; }
+};
+
+// Returns nullptr for an out-of-range code.
+const CodeInfo *code_info(int code);
+
+// Ordered edge list (reference order): check[idx], var[idx].
+void expand_edges(const CodeInfo &c, std::vector<uint32_t> &check, std::vector<uint32_t> &var);
+
+// CRC-32 over the ordered edge list as in reference src/codes/mod.rs:508-535.
+uint32_t edge_crc(const CodeInfo &c);
+
+// ELL tables for the generic kernels.
+//   var_tab[j*vars + a]   = idx | check << 16   j-th edge of variable a in ascending idx order
+//   chk_tab[j*checks + c] = idx | var   << 16   j-th edge of check c in ascending idx order
+// Missing entries are kNoEdge.
+void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::vector<uint32_t> &chk_tab);
+
+}  // namespace ldpc

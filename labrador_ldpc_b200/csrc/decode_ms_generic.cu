@@ -1,0 +1,216 @@
+// Generic batched min-sum decoder: any code, any LLR type.
+//
+// Replaces LDPCCode::decode_ms<T> (reference src/decoder.rs:347-475) for every
+// (code, T) pair that has no specialised kernel.  One CTA decodes one codeword
+// at a time.  The reference's two edge loops per iteration are re-expressed as
+//   phase A (one thread per variable):  recompute u for the variable's edges
+//            from the previous v and the previous per-check (min1, min2, sign)
+//            (src/decoder.rs:391-405), accumulate the marginal with saturating
+//            adds in ascending edge order (:408 -- the only order-sensitive
+//            operation), then produce the self-corrected new v for each edge
+//            (:421-426);
+//   phase B (one thread per check):  min1/min2 of |v|, sign product and the
+//            parity of the marginals' hard bits (:430-447), followed by the
+//            all-parities-zero exit test (:453).
+// u is never stored: it is a pure function of the old v and the old per-check
+// state, so the state is v[E] + min1[C] + min2[C] + sign[C] (+ hard bits).
+// v lives in shared memory when it fits, else in an L2-resident global scratch
+// slot owned by the CTA.
+#include <cuda_runtime.h>
+
+#include "llr_arith.cuh"
+#include "runtime.h"
+
+namespace ldpc {
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kMaxVarDeg = 6;
+
+struct MsLayout {
+    // byte offsets into dynamic shared memory
+    unsigned v_off, min1_off, min2_off, llr_off, sgn_off, hb_off, total;
+    bool v_in_smem, llr_in_smem;
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads)
+decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay, const T *__restrict__ llrs_all,
+                         uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
+                         uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
+                         T *__restrict__ vscratch) {
+    typedef Arith<T> A;
+    extern __shared__ __align__(16) unsigned char smem[];
+    T *v = lay.v_in_smem ? reinterpret_cast<T *>(smem + lay.v_off)
+                         : vscratch + (size_t)blockIdx.x * code.edges;
+    T *min1 = reinterpret_cast<T *>(smem + lay.min1_off);
+    T *min2 = reinterpret_cast<T *>(smem + lay.min2_off);
+    T *llr_s = reinterpret_cast<T *>(smem + lay.llr_off);
+    uint8_t *sgn = smem + lay.sgn_off;
+    uint8_t *hb = smem + lay.hb_off;
+
+    const int tid = threadIdx.x;
+    const int n = code.n, nv = code.vars, nc = code.checks, ne = code.edges;
+    const int dv = code.max_var_degree, dc = code.max_check_degree;
+    const int out_len = nv / 8;
+
+    for (unsigned long long frame = blockIdx.x; frame < batch; frame += gridDim.x) {
+        const T *llr_g = llrs_all + frame * (unsigned long long)n;
+        // Zero-initialised state, every call (reference :368, :374).
+        for (int i = tid; i < ne; i += kThreads) v[i] = A::zero();
+        for (int i = tid; i < nc; i += kThreads) { min1[i] = A::zero(); min2[i] = A::zero(); sgn[i] = 0; }
+        for (int i = tid; i < nv; i += kThreads) hb[i] = 0;
+        if (lay.llr_in_smem)
+            for (int i = tid; i < n; i += kThreads) llr_s[i] = llr_g[i];
+        const T *llr = lay.llr_in_smem ? llr_s : llr_g;
+        __syncthreads();
+
+        unsigned iters_run = max_iters;
+        bool ok = false;
+        for (unsigned iter = 0; iter < max_iters; iter++) {
+            // ---- phase A: variables ----
+            for (int a = tid; a < nv; a += kThreads) {
+                T va = a < n ? llr[a] : A::zero();                          // :382-383
+                T ul[kMaxVarDeg];
+                T vold[kMaxVarDeg];
+#pragma unroll
+                for (int j = 0; j < kMaxVarDeg; j++) {
+                    ul[j] = A::zero(); vold[j] = A::zero();
+                    if (j < dv) {
+                        const uint32_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
+                        if (ent != kNoEdge) {
+                            const int idx = ent & 0xFFFF, c = ent >> 16;
+                            const T vv = v[idx];
+                            T u = (A::abs(vv) == min1[c]) ? min2[c] : min1[c];   // :391-395
+                            if (sgn[c]) u = A::neg(u);                           // :398-400
+                            if (A::hard_bit(vv)) u = A::neg(u);                  // :403-405
+                            va = A::sat_add(va, u);                              // :408
+                            ul[j] = u; vold[j] = vv;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kMaxVarDeg; j++) {
+                    if (j < dv) {
+                        const uint32_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
+                        if (ent != kNoEdge) {
+                            const int idx = ent & 0xFFFF;
+                            const T nvv = A::sat_sub(va, ul[j]);                 // :421
+                            const bool keep = (A::hard_bit(nvv) == A::hard_bit(vold[j])) || (vold[j] == A::zero());
+                            v[idx] = keep ? nvv : A::zero();                     // :422-426
+                        }
+                    }
+                }
+                hb[a] = A::hard_bit(va) ? 1 : 0;
+            }
+            __syncthreads();
+            // ---- phase B: checks ----
+            int par_any = 0;
+            for (int c = tid; c < nc; c += kThreads) {
+                T m1 = A::maxval(), m2 = A::maxval();                       // :414-415
+                int s = 0, par = 0;
+                for (int j = 0; j < dc; j++) {
+                    const uint32_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
+                    if (ent == kNoEdge) break;
+                    const int idx = ent & 0xFFFF, var = ent >> 16;
+                    const T vv = v[idx];
+                    const T av = A::abs(vv);
+                    if (av < m1) { m2 = m1; m1 = av; }                      // :430-435
+                    else if (av < m2) { m2 = av; }
+                    s ^= A::hard_bit(vv) ? 1 : 0;                           // :439-441
+                    par ^= hb[var];                                         // :445-447
+                }
+                min1[c] = m1; min2[c] = m2; sgn[c] = (uint8_t)s;
+                par_any |= par;
+            }
+            if (__syncthreads_or(par_any) == 0) {                           // :453
+                ok = true; iters_run = iter;                                // :462
+                break;
+            }
+        }
+        // Hard decisions of all n+p marginals, MSB first (:455-461, :466-473).
+        uint8_t *out = out_all + frame * (unsigned long long)out_len;
+        for (int o = tid; o < out_len; o += kThreads) {
+            unsigned byte = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) byte |= (unsigned)hb[o * 8 + b] << (7 - b);
+            out[o] = (uint8_t)byte;
+        }
+        if (tid == 0) {
+            if (success) success[frame] = ok ? 1 : 0;
+            if (iters_out) iters_out[frame] = iters_run;
+        }
+        __syncthreads();
+    }
+}
+
+inline unsigned align16(unsigned x) { return (x + 15u) & ~15u; }
+
+template <class T>
+MsLayout make_layout(const DeviceCode &c, int max_smem) {
+    MsLayout l{};
+    const unsigned ts = sizeof(T);
+    const unsigned fixed = align16(c.checks * ts) * 2 + align16(c.checks) + align16(c.vars);
+    const unsigned vbytes = align16(c.edges * ts);
+    const unsigned lbytes = align16(c.n * ts);
+    l.v_in_smem = fixed + vbytes <= (unsigned)max_smem;
+    l.llr_in_smem = fixed + (l.v_in_smem ? vbytes : 0) + lbytes <= (unsigned)max_smem;
+    unsigned off = 0;
+    l.v_off = off; if (l.v_in_smem) off += vbytes;
+    l.min1_off = off; off += align16(c.checks * ts);
+    l.min2_off = off; off += align16(c.checks * ts);
+    l.llr_off = off; if (l.llr_in_smem) off += lbytes;
+    l.sgn_off = off; off += align16(c.checks);
+    l.hb_off = off; off += align16(c.vars);
+    l.total = off;
+    return l;
+}
+
+template <class T>
+cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
+                           size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    const DeviceCode &dc = ctx.codes[code];
+    const MsLayout lay = make_layout<T>(dc, ctx.max_smem_optin);
+    auto kern = decode_ms_generic_kernel<T>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
+    if (err != cudaSuccess) return err;
+    unsigned long long grid = batch;
+    T *scratch = nullptr;
+    if (!lay.v_in_smem) {
+        // persistent CTAs, one global message slot each
+        grid = (unsigned long long)ctx.sm_count;
+        if (grid > batch) grid = batch;
+        const size_t need = (size_t)grid * dc.edges * sizeof(T);
+        if (ctx.vscratch_bytes < need) {
+            if (ctx.vscratch) cudaFree(ctx.vscratch);
+            ctx.vscratch = nullptr; ctx.vscratch_bytes = 0;
+            err = cudaMalloc(&ctx.vscratch, need);
+            if (err != cudaSuccess) return err;
+            ctx.vscratch_bytes = need;
+        }
+        scratch = static_cast<T *>(ctx.vscratch);
+    }
+    if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
+    const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
+    kern<<<(unsigned)grid, kThreads, lay.total, stream>>>(dc, lay, static_cast<const T *>(llrs), output,
+                                                          (unsigned long long)batch, mi, success, iters, scratch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_decode_ms_generic(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
+                                     size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
+                                     cudaStream_t stream) {
+    switch (llr_type) {
+        case kI8: return launch_generic<int8_t>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);
+        case kI16: return launch_generic<int16_t>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);
+        case kI32: return launch_generic<int32_t>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);
+        case kF32: return launch_generic<float>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);
+        case kF64: return launch_generic<double>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace ldpc

@@ -1,0 +1,384 @@
+// Device contexts, device-resident tables, kernel dispatch and the
+// host-buffer streaming pipeline behind the `_batch` C entry points.
+#include "runtime.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "host_api.h"
+
+namespace ldpc {
+
+// implemented in decode_ms_generic.cu / decode_ms_tm.cu
+cudaError_t launch_decode_ms_generic(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
+                                     size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
+                                     cudaStream_t stream);
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+thread_local std::string t_last_error;
+
+struct Runtime {
+    std::mutex mu;
+    bool inited = false;
+    std::vector<int> devices;                          // devices used for host-pointer batches
+    std::vector<std::unique_ptr<DeviceCtx>> ctxs;      // every context created so far
+    std::vector<std::unique_ptr<std::mutex>> ctx_mu;   // serialises pipeline use per context
+};
+
+Runtime &rt() {
+    static Runtime r;
+    return r;
+}
+
+int set_error(int code, const std::string &msg) {
+    t_last_error = msg;
+    return code;
+}
+
+int cuda_error(cudaError_t e, const char *what) {
+    return set_error(LDPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                    \
+    do {                                                  \
+        cudaError_t e__ = (expr);                         \
+        if (e__ != cudaSuccess) return cuda_error(e__, #expr); \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Builds every device table of every code in one blob (one cudaMalloc + one copy).
+int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<DeviceCtx> ctx(new DeviceCtx());
+    ctx->device = device;
+    CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+
+    std::vector<unsigned char> blob;
+    struct Off { size_t var_tab, chk_tab, gen, gen32; };
+    Off offs[kNumCodes];
+    for (int ci = 0; ci < kNumCodes; ci++) {
+        const CodeInfo &c = *code_info(ci);
+        std::vector<uint32_t> vt, ct;
+        build_ell_tables(c, vt, ct);
+        auto append = [&blob](const void *p, size_t bytes) {
+            const size_t off = align_up(blob.size(), 256);
+            blob.resize(off + bytes);
+            memcpy(blob.data() + off, p, bytes);
+            return off;
+        };
+        offs[ci].var_tab = append(vt.data(), vt.size() * 4);
+        offs[ci].chk_tab = append(ct.data(), ct.size() * 4);
+        const size_t gwords = (size_t)(c.k / c.b) * ((c.n - c.k) / 64);
+        offs[ci].gen = append(c.gen, gwords * 8);
+        std::vector<uint32_t> g32(gwords * 2);
+        for (size_t i = 0; i < gwords; i++) {
+            g32[2 * i] = (uint32_t)(c.gen[i] >> 32);
+            g32[2 * i + 1] = (uint32_t)(c.gen[i] & 0xFFFFFFFFu);
+        }
+        offs[ci].gen32 = append(g32.data(), g32.size() * 4);
+    }
+    CUDA_TRY(cudaMalloc(&ctx->table_blob, blob.size()));
+    CUDA_TRY(cudaMemcpy(ctx->table_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    const unsigned char *base = static_cast<const unsigned char *>(ctx->table_blob);
+    for (int ci = 0; ci < kNumCodes; ci++) {
+        const CodeInfo &c = *code_info(ci);
+        DeviceCode &d = ctx->codes[ci];
+        d.n = c.n; d.k = c.k; d.p = c.p; d.m = c.m; d.b = c.b;
+        d.edges = c.edges; d.checks = c.checks; d.vars = c.vars;
+        d.max_var_degree = c.max_var_degree; d.max_check_degree = c.max_check_degree;
+        d.n_blocks = c.n_blocks;
+        d.var_tab = reinterpret_cast<const uint32_t *>(base + offs[ci].var_tab);
+        d.chk_tab = reinterpret_cast<const uint32_t *>(base + offs[ci].chk_tab);
+        d.gen = reinterpret_cast<const uint64_t *>(base + offs[ci].gen);
+        d.gen32 = reinterpret_cast<const uint32_t *>(base + offs[ci].gen32);
+    }
+    for (int i = 0; i < DeviceCtx::kPipe; i++)
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
+    out = std::move(ctx);
+    return LDPC_OK;
+}
+
+// Caller holds rt().mu.
+int ctx_for_device_locked(int device, DeviceCtx **out, std::mutex **mu_out) {
+    Runtime &r = rt();
+    for (size_t i = 0; i < r.ctxs.size(); i++)
+        if (r.ctxs[i]->device == device) {
+            *out = r.ctxs[i].get();
+            if (mu_out) *mu_out = r.ctx_mu[i].get();
+            return LDPC_OK;
+        }
+    std::unique_ptr<DeviceCtx> ctx;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    const int rc = build_ctx(device, ctx);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (rc != LDPC_OK) return rc;
+    r.ctxs.push_back(std::move(ctx));
+    r.ctx_mu.emplace_back(new std::mutex());
+    *out = r.ctxs.back().get();
+    if (mu_out) *mu_out = r.ctx_mu.back().get();
+    return LDPC_OK;
+}
+
+}  // namespace
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+const char *last_error() { return t_last_error.c_str(); }
+int fail(int code, const char *msg) { return set_error(code, msg); }
+
+int runtime_init(const int *devices, int n_devices) {
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> lock(r.mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_error(e, "cudaGetDeviceCount");
+    if (count == 0) return set_error(LDPC_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    std::vector<int> want;
+    if (devices == nullptr || n_devices <= 0) {
+        if (r.inited) return LDPC_OK;
+        int cur = 0;
+        CUDA_TRY(cudaGetDevice(&cur));
+        want.push_back(cur);
+    } else {
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= count)
+                return set_error(LDPC_ERR_BAD_ARGUMENT, "device index out of range");
+            want.push_back(devices[i]);
+        }
+    }
+    for (int d : want) {
+        DeviceCtx *ctx = nullptr;
+        const int rc = ctx_for_device_locked(d, &ctx, nullptr);
+        if (rc != LDPC_OK) return rc;
+    }
+    r.devices = want;
+    r.inited = true;
+    return LDPC_OK;
+}
+
+void runtime_shutdown() {
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> lock(r.mu);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto &c : r.ctxs) {
+        cudaSetDevice(c->device);
+        for (int i = 0; i < DeviceCtx::kPipe; i++) {
+            if (c->pipe_stream[i]) { cudaStreamSynchronize(c->pipe_stream[i]); cudaStreamDestroy(c->pipe_stream[i]); }
+            if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
+        }
+        if (c->vscratch) cudaFree(c->vscratch);
+        if (c->table_blob) cudaFree(c->table_blob);
+    }
+    r.ctxs.clear();
+    r.ctx_mu.clear();
+    r.devices.clear();
+    r.inited = false;
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+int runtime_device_count() {
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> lock(r.mu);
+    return (int)r.devices.size();
+}
+
+int get_ctx(int device, DeviceCtx **out, std::mutex **mu_out) {
+    int rc = runtime_init(nullptr, 0);
+    if (rc != LDPC_OK) return rc;
+    Runtime &r = rt();
+    std::lock_guard<std::mutex> lock(r.mu);
+    return ctx_for_device_locked(device, out, mu_out);
+}
+
+// 0 = host (pageable or pinned), 1 = device/managed; *device receives the owning device.
+int classify_pointer(const void *p, int *device) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+        if (device) *device = attr.device;
+        return 1;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------
+cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
+                             size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
+                             cudaStream_t stream) {
+    if (batch == 0) return cudaSuccess;
+    return launch_decode_ms_generic(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream);
+}
+
+const char *decode_ms_kernel_name(int code, int llr_type) {
+    (void)code;
+    static const char *names[kNumLlrTypes] = {"ms_generic<i8>", "ms_generic<i16>", "ms_generic<i32>",
+                                              "ms_generic<f32>", "ms_generic<f64>"};
+    if (llr_type < 0 || llr_type >= kNumLlrTypes) return "invalid";
+    return names[llr_type];
+}
+
+// ---------------------------------------------------------------------------
+// Host-buffer pipeline: frames are streamed through the GPU in chunks; chunk c
+// uses buffer/stream c % 3, so the H2D copy of one chunk, the kernel of the
+// previous one and the D2H copy of the one before overlap.
+// ---------------------------------------------------------------------------
+namespace {
+
+size_t chunk_bytes_target() {
+    static size_t v = [] {
+        const char *e = getenv("LABRADOR_LDPC_CHUNK_MB");
+        size_t mb = e ? (size_t)atol(e) : 32;
+        if (mb < 1) mb = 1;
+        return mb << 20;
+    }();
+    return v;
+}
+
+int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<HostArray> &arrays, size_t first,
+                            size_t count, const BatchLaunch &launch) {
+    std::lock_guard<std::mutex> lock(mu);
+    CUDA_TRY(cudaSetDevice(ctx.device));
+    size_t per_frame = 0;
+    for (const HostArray &a : arrays) per_frame += align_up(a.bytes_per_frame, 16);
+    if (per_frame == 0 || count == 0) return LDPC_OK;
+    size_t chunk = chunk_bytes_target() / per_frame;
+    const size_t min_chunk = (size_t)ctx.sm_count * 8;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > count) chunk = count;
+    // carve one device buffer per pipeline slot
+    std::vector<size_t> offs(arrays.size());
+    size_t total = 0;
+    for (size_t i = 0; i < arrays.size(); i++) {
+        offs[i] = total;
+        total += align_up(arrays[i].bytes_per_frame * chunk, 256);
+    }
+    const size_t n_chunks = (count + chunk - 1) / chunk;
+    const int slots = (int)(n_chunks < (size_t)DeviceCtx::kPipe ? n_chunks : (size_t)DeviceCtx::kPipe);
+    for (int s = 0; s < slots; s++) {
+        if (ctx.pipe_bytes[s] < total) {
+            if (ctx.pipe_buf[s]) { CUDA_TRY(cudaStreamSynchronize(ctx.pipe_stream[s])); CUDA_TRY(cudaFree(ctx.pipe_buf[s])); }
+            ctx.pipe_buf[s] = nullptr; ctx.pipe_bytes[s] = 0;
+            CUDA_TRY(cudaMalloc(&ctx.pipe_buf[s], total));
+            ctx.pipe_bytes[s] = total;
+        }
+    }
+    int rc = LDPC_OK;
+    for (size_t c = 0; c < n_chunks && rc == LDPC_OK; c++) {
+        const int s = (int)(c % DeviceCtx::kPipe);
+        cudaStream_t st = ctx.pipe_stream[s];
+        unsigned char *base = static_cast<unsigned char *>(ctx.pipe_buf[s]);
+        const size_t f0 = first + c * chunk;
+        const size_t nf = (c + 1 == n_chunks) ? (count - c * chunk) : chunk;
+        std::vector<void *> dptr(arrays.size());
+        for (size_t i = 0; i < arrays.size(); i++) {
+            const HostArray &a = arrays[i];
+            dptr[i] = base + offs[i];
+            if (a.host_in) {
+                const unsigned char *src = static_cast<const unsigned char *>(a.host_in) + f0 * a.bytes_per_frame;
+                cudaError_t e = cudaMemcpyAsync(dptr[i], src, nf * a.bytes_per_frame, cudaMemcpyHostToDevice, st);
+                if (e != cudaSuccess) { rc = cuda_error(e, "H2D copy"); break; }
+            }
+        }
+        if (rc != LDPC_OK) break;
+        cudaError_t e = launch(ctx, dptr, nf, st);
+        if (e != cudaSuccess) { rc = cuda_error(e, "kernel launch"); break; }
+        for (size_t i = 0; i < arrays.size(); i++) {
+            const HostArray &a = arrays[i];
+            if (a.host_out) {
+                unsigned char *dst = static_cast<unsigned char *>(a.host_out) + f0 * a.bytes_per_frame;
+                e = cudaMemcpyAsync(dst, dptr[i], nf * a.bytes_per_frame, cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess) { rc = cuda_error(e, "D2H copy"); break; }
+            }
+        }
+    }
+    for (int s = 0; s < slots; s++) {
+        cudaError_t e = cudaStreamSynchronize(ctx.pipe_stream[s]);
+        if (e != cudaSuccess && rc == LDPC_OK) rc = cuda_error(e, "stream synchronize");
+    }
+    return rc;
+}
+
+}  // namespace
+
+int run_host_batch(const std::vector<HostArray> &arrays, size_t batch, const BatchLaunch &launch) {
+    if (batch == 0) return LDPC_OK;
+    int rc = runtime_init(nullptr, 0);
+    if (rc != LDPC_OK) return rc;
+    std::vector<int> devices;
+    {
+        Runtime &r = rt();
+        std::lock_guard<std::mutex> lock(r.mu);
+        devices = r.devices;
+    }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    const size_t nd = devices.size();
+    if (nd <= 1 || batch < nd) {
+        DeviceCtx *ctx = nullptr;
+        std::mutex *mu = nullptr;
+        rc = get_ctx(devices.empty() ? 0 : devices[0], &ctx, &mu);
+        if (rc == LDPC_OK) rc = run_on_device_host_ptrs(*ctx, *mu, arrays, 0, batch, launch);
+    } else {
+        // contiguous shards of independent codewords, one host thread per device, no collective
+        std::vector<int> rcs(nd, LDPC_OK);
+        std::vector<std::string> errs(nd);
+        std::vector<std::thread> threads;
+        for (size_t g = 0; g < nd; g++) {
+            const size_t f0 = batch * g / nd, f1 = batch * (g + 1) / nd;
+            threads.emplace_back([&, g, f0, f1]() {
+                DeviceCtx *ctx = nullptr;
+                std::mutex *mu = nullptr;
+                int r2 = get_ctx(devices[g], &ctx, &mu);
+                if (r2 == LDPC_OK) r2 = run_on_device_host_ptrs(*ctx, *mu, arrays, f0, f1 - f0, launch);
+                rcs[g] = r2;
+                if (r2 != LDPC_OK) errs[g] = last_error();
+            });
+        }
+        for (auto &t : threads) t.join();
+        for (size_t g = 0; g < nd; g++)
+            if (rcs[g] != LDPC_OK) { rc = set_error(rcs[g], errs[g]); break; }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    return rc;
+}
+
+int run_device_batch(int device, cudaStream_t stream, bool synchronize,
+                     const std::function<cudaError_t(DeviceCtx &, cudaStream_t)> &launch) {
+    DeviceCtx *ctx = nullptr;
+    std::mutex *mu = nullptr;
+    int rc = get_ctx(device, &ctx, &mu);
+    if (rc != LDPC_OK) return rc;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != device) CUDA_TRY(cudaSetDevice(device));
+    cudaError_t e;
+    {
+        std::lock_guard<std::mutex> lock(*mu);   // launchers may grow per-context scratch
+        e = launch(*ctx, stream);
+    }
+    if (e == cudaSuccess && synchronize) e = cudaStreamSynchronize(stream);
+    if (prev != device && prev >= 0) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_error(e, "device batch");
+    return LDPC_OK;
+}
+
+}  // namespace ldpc

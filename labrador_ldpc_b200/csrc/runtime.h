@@ -1,0 +1,76 @@
+// Internal interfaces of the B200 LDPC library: per-device context, device
+// tables and the kernel launchers.  Nothing here crosses the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "code_tables.h"
+
+namespace ldpc {
+
+enum LlrType : int { kI8 = 0, kI16 = 1, kI32 = 2, kF32 = 3, kF64 = 4, kNumLlrTypes = 5 };
+
+inline size_t llr_size(int t) {
+    switch (t) {
+        case kI8: return 1;
+        case kI16: return 2;
+        case kI32: return 4;
+        case kF32: return 4;
+        case kF64: return 8;
+        default: return 0;
+    }
+}
+
+// Device-resident tables of one code (built once per device by DeviceCtx).
+struct DeviceCode {
+    int n, k, p, m, b;
+    int edges, checks, vars;
+    int max_var_degree, max_check_degree;
+    int n_blocks;
+    const uint32_t *var_tab;   // [max_var_degree][vars]   idx | check << 16
+    const uint32_t *chk_tab;   // [max_check_degree][checks] idx | var << 16
+    const uint64_t *gen;       // compact generator rows
+    const uint32_t *gen32;     // same rows as big-endian-ordered 32-bit words
+};
+
+struct DeviceCtx {
+    int device = -1;
+    int sm_count = 0;
+    int max_smem_optin = 0;       // bytes of dynamic shared memory a CTA may opt in to
+    DeviceCode codes[kNumCodes];
+    void *table_blob = nullptr;   // one allocation holding every table
+    // scratch for decode paths whose message array does not fit in shared memory
+    void *vscratch = nullptr;
+    size_t vscratch_bytes = 0;
+    // host-pointer pipeline
+    static constexpr int kPipe = 3;
+    cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
+    void *pipe_buf[kPipe] = {nullptr, nullptr, nullptr};
+    size_t pipe_bytes[kPipe] = {0, 0, 0};
+};
+
+// Global launch counter (every kernel launch of this library increments it).
+void count_launch(int n = 1);
+
+// ---- kernel launchers (device pointers, stream-ordered, no synchronisation) ----
+cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
+                             size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
+                             cudaStream_t stream);
+const char *decode_ms_kernel_name(int code, int llr_type);
+
+cudaError_t launch_decode_bf(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
+                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream);
+
+// codewords: [batch][n/8]; if data != nullptr it is [batch][k/8] and is copied in first.
+cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t *codewords, size_t batch,
+                          cudaStream_t stream);
+
+cudaError_t launch_hard_to_llrs(DeviceCtx &ctx, int code, int llr_type, const uint8_t *input, void *llrs,
+                                size_t batch, cudaStream_t stream);
+cudaError_t launch_llrs_to_hard(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
+                                size_t batch, cudaStream_t stream);
+
+}  // namespace ldpc

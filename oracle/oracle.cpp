@@ -86,6 +86,7 @@ inline void for_each_edge(const Params &c, F &&f) {
     const int q = m / 4;
     int logq = 0;
     while ((1 << logq) < q) logq++;
+    int idx = 0;   // running edge index (the reference's `idx += 1`, src/decoder.rs:410,449)
     for (int row = 0; row < 4; row++) {
         for (int col = 0; col < 11; col++) {
             for (int sub = 0; sub < 3; sub++) {
@@ -94,14 +95,14 @@ inline void for_each_edge(const Params &c, F &&f) {
                 const int val = e & CCSDS_VAL_MASK;
                 const int kind = e & CCSDS_KIND_MASK;
                 if (kind == CCSDS_KIND_IDENT) {
-                    for (int i = 0; i < m; i++)
-                        f(row * m + i, col * m + ((i + val) & (m - 1)));
+                    for (int i = 0; i < m; i++, idx++)
+                        f(idx, row * m + i, col * m + ((i + val) & (m - 1)));
                 } else if (kind == CCSDS_KIND_PERM) {
-                    for (int i = 0; i < m; i++) {
+                    for (int i = 0; i < m; i++, idx++) {
                         const int j = i >> logq;
                         const int pi = (((ccsds_theta_k[val] + j) % 4) << logq) +
                                        ((c.phi[j * 26 + val] + i) & (q - 1));
-                        f(row * m + i, col * m + pi);
+                        f(idx, row * m + i, col * m + pi);
                     }
                 }
             }
@@ -312,35 +313,35 @@ bool decode_ms(const Params &c, const T *llrs, uint8_t *output, T *working, uint
         for (int i = 0; i < n; i++) va[i] = llrs[i];              // :382
         for (int i = n; i < n + p; i++) va[i] = O::zero();        // :383
 
-        size_t idx = 0;                                           // :387
-        for_each_edge(c, [&](int check, int var) {                // :388
-            if (O::abs(v[idx]) == ui_min1[check]) u[idx] = ui_min2[check];   // :391-395
-            else u[idx] = ui_min1[check];
-            if ((ui_sgns[check / 8] >> (check % 8)) & 1) u[idx] = O::neg(u[idx]);  // :398-400
-            if (O::hard_bit(v[idx])) u[idx] = O::neg(u[idx]);     // :403-405
-            va[var] = O::sat_add(va[var], u[idx]);                // :408
-            idx++;
+        for_each_edge(c, [=](int idx, int check, int var) {       // :387-388
+            // (locals + conditional expressions instead of repeated u[idx] stores so the
+            // compiler can emit selects, as rustc does; same operations in the same order)
+            const T vi = v[idx];
+            const T m1 = ui_min1[check];
+            T uu = (O::abs(vi) == m1) ? ui_min2[check] : m1;              // :391-395
+            uu = ((ui_sgns[check / 8] >> (check % 8)) & 1) ? O::neg(uu) : uu;  // :398-400
+            uu = O::hard_bit(vi) ? O::neg(uu) : uu;                       // :403-405
+            u[idx] = uu;
+            va[var] = O::sat_add(va[var], uu);                            // :408
         });
 
         for (size_t i = 0; i < nchk; i++) ui_min1[i] = O::maxval();   // :414
         for (size_t i = 0; i < nchk; i++) ui_min2[i] = O::maxval();   // :415
         for (size_t i = 0; i < ms_working_u8_len(c); i++) ui_sgns[i] = 0;  // :416
         for (size_t i = 0; i < olen; i++) parities[i] = 0;        // :417
-        idx = 0;
-        for_each_edge(c, [&](int check, int var) {                // :419
-            const T new_v = O::sat_sub(va[var], u[idx]);          // :421
-            if (O::hard_bit(new_v) == O::hard_bit(v[idx]) || v[idx] == O::zero()) v[idx] = new_v;
-            else v[idx] = O::zero();                              // :422-426
-            const T a = O::abs(v[idx]);
-            if (a < ui_min1[check]) {                             // :430-435
-                ui_min2[check] = ui_min1[check];
-                ui_min1[check] = a;
-            } else if (a < ui_min2[check]) {
-                ui_min2[check] = a;
-            }
-            if (O::hard_bit(v[idx])) ui_sgns[check / 8] ^= (uint8_t)(1 << (check % 8));   // :439-441
-            if (O::hard_bit(va[var])) parities[check / 8] ^= (uint8_t)(1 << (check % 8)); // :445-447
-            idx++;
+        for_each_edge(c, [=](int idx, int check, int var) {       // :419
+            const T vav = va[var];
+            const T vold = v[idx];
+            const T new_v = O::sat_sub(vav, u[idx]);              // :421
+            const T vn = (O::hard_bit(new_v) == O::hard_bit(vold) || vold == O::zero())
+                             ? new_v : O::zero();                 // :422-426
+            v[idx] = vn;
+            const T a = O::abs(vn);
+            const T m1 = ui_min1[check], m2 = ui_min2[check];     // :430-435
+            ui_min1[check] = (a < m1) ? a : m1;
+            ui_min2[check] = (a < m1) ? m1 : ((a < m2) ? a : m2);
+            ui_sgns[check / 8] ^= (uint8_t)((O::hard_bit(vn) ? 1 : 0) << (check % 8));    // :439-441
+            parities[check / 8] ^= (uint8_t)((O::hard_bit(vav) ? 1 : 0) << (check % 8));  // :445-447
         });
 
         uint8_t mx = 0;                                           // :453
@@ -372,7 +373,7 @@ bool decode_erasures(const Params &c, uint8_t *codeword, uint8_t *working, size_
     int bits_fixed = 0;                                           // :170
     for (size_t iter = 0; iter < maxiters; iter++) {
         for (int i = 0; i < n + p; i++) working[i] = (working[i] & 0x10) | 0x08;  // :174
-        for_each_edge(c, [&](int check, int var) {                // :177-189
+        for_each_edge(c, [&](int, int check, int var) {                // :177-189
             if ((working[var] & 0x10) == 0x10) {
                 switch (working[check] & 0x60) {
                     case 0x00: working[check] |= 0x20; break;
@@ -383,7 +384,7 @@ bool decode_erasures(const Params &c, uint8_t *codeword, uint8_t *working, size_
                 working[check] ^= 0x80;
             }
         });
-        for_each_edge(c, [&](int check, int var) {                // :192-202
+        for_each_edge(c, [&](int, int check, int var) {                // :192-202
             if ((working[var] & 0x10) == 0x10 && (working[check] & 0x60) == 0x20) {
                 if ((working[check] & 0x80) == 0x80) working[var] += 1;
                 else working[var] -= 1;
@@ -418,11 +419,11 @@ bool decode_bf(const Params &c, const uint8_t *input, uint8_t *output, uint8_t *
     if (p > 0) decode_erasures(c, output, working, maxiters, &erasure_iters);
     for (size_t iter = 0; iter < maxiters; iter++) {              // :264
         for (int i = 0; i < n + p; i++) working[i] = 0;           // :266
-        for_each_edge(c, [&](int check, int var) {                // :269-273
+        for_each_edge(c, [&](int, int check, int var) {                // :269-273
             if ((output[var / 8] >> (7 - (var % 8))) & 1) working[check] ^= 0x80;
         });
         uint8_t max_violations = 0;                               // :276-286
-        for_each_edge(c, [&](int check, int var) {
+        for_each_edge(c, [&](int, int check, int var) {
             if ((working[check] & 0x80) == 0x80) {
                 working[var] += 1;
                 if ((working[var] & 0x7F) > max_violations) max_violations = working[var] & 0x7F;
@@ -463,7 +464,9 @@ template <class F> void parallel_frames(size_t batch, int nthreads, F &&f) {
         return;
     }
     std::atomic<size_t> next(0);
-    const size_t chunk = 16;
+    size_t chunk = batch / ((size_t)nthreads * 8);
+    if (chunk < 1) chunk = 1;
+    if (chunk > 16) chunk = 16;
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++) {
         th.emplace_back([&, t]() {
@@ -528,7 +531,7 @@ int oracle_edges(int code, uint32_t *checks, uint32_t *vars, uint32_t *crc_out) 
     if (!valid(code)) return -1;
     int count = 0;
     uint32_t crc = 0xFFFFFFFFu;
-    for_each_edge(PARAMS[code], [&](int check, int var) {
+    for_each_edge(PARAMS[code], [&](int, int check, int var) {
         if (checks) checks[count] = (uint32_t)check;
         if (vars) vars[count] = (uint32_t)var;
         crc = crc32_u16(crc, (uint32_t)check);

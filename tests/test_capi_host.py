@@ -1,0 +1,168 @@
+"""CPU-side checks of the product library: it loads, exports every symbol the header
+declares, and its host logic (size getters, table expansion, argument validation) is right.
+No compute call succeeds here (no GPU in this container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = ["TC128", "TC256", "TC512", "TM1280", "TM1536", "TM2048", "TM5120", "TM6144", "TM8192"]
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "labrador_ldpc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(labrador_ldpc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(ldpc):
+    syms = header_symbols()
+    assert len(syms) >= 21 + 20
+    for s in syms:
+        assert hasattr(ldpc.lib, s), s
+    # the reference's 21 entry points (capi/src/lib.rs:15-179)
+    ref21 = ["code_n", "code_k", "encode", "copy_encode", "bf_working_len", "ms_working_len",
+             "ms_working_u8_len", "output_len", "decode_bf"]
+    for t in ("i8", "i16", "f32", "f64"):
+        ref21 += ["decode_ms_" + t, "hard_to_llrs_" + t, "llrs_to_hard_" + t]
+    assert len(ref21) == 21
+    for s in ref21:
+        assert "labrador_ldpc_" + s in syms
+
+
+def test_size_getters_match_reference_table(ldpc, kats):
+    for code, name in enumerate(NAMES):
+        P = kats["params"][name]
+        c = ldpc.LDPCCode(code)
+        assert c.n() == P["n"] and c.k() == P["k"]
+        assert c.punctured_bits() == P["punctured_bits"]
+        assert c.paritycheck_sum() == P["paritycheck_sum"]
+        assert c.decode_bf_working_len() == P["decode_bf_working_len"]
+        assert c.decode_ms_working_len() == P["decode_ms_working_len"]
+        assert c.decode_ms_working_u8_len() == P["decode_ms_working_u8_len"]
+        assert c.output_len() == P["output_len"]
+    assert ldpc.lib.labrador_ldpc_code_n(9) == 0 and ldpc.lib.labrador_ldpc_code_n(-1) == 0
+
+
+def test_edge_table_crc_goldens(ldpc, kats):
+    # the device edge tables are expanded from the same block list; its CRC must hit
+    # the reference's goldens (src/codes/mod.rs:521-523)
+    for code in range(9):
+        assert ldpc.LDPCCode(code).edge_table_crc() == kats["edge_crc32"][code]
+
+
+def test_header_macros_compile_and_match(kats, tmp_path):
+    # compile a C program against include/labrador_ldpc.h and compare every size macro
+    # (incl. the reference's misspelt _TM6140 names) with the reference's literal table
+    lines = ['#include "labrador_ldpc.h"', "#include <stdio.h>", "int main(void){"]
+    for name in NAMES + ["TM6140"]:
+        for mac in ("N", "K", "BF_WORKING_LEN", "MS_WORKING_LEN", "MS_WORKING_U8_LEN", "OUTPUT_LEN"):
+            lines.append('printf("%s_%s %%d\\n", (int)LABRADOR_LDPC_%s_%s);' % (mac, name, mac, name))
+    lines.append('printf("GEN %d %d\\n", (int)LABRADOR_LDPC_MS_WORKING_LEN(TM8192), (int)LABRADOR_LDPC_CODE(TM2048));')
+    lines.append("return 0;}")
+    src = tmp_path / "m.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "m"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines() if not l.startswith("GEN"))
+    field = {"N": "n", "K": "k", "BF_WORKING_LEN": "decode_bf_working_len", "MS_WORKING_LEN": "decode_ms_working_len",
+             "MS_WORKING_U8_LEN": "decode_ms_working_u8_len", "OUTPUT_LEN": "output_len"}
+    for name in NAMES + ["TM6140"]:
+        P = kats["params"]["TM6144" if name == "TM6140" else name]
+        for mac, f in field.items():
+            assert int(out["%s_%s" % (mac, name)]) == P[f], (mac, name)
+    # every macro the reference header defines exists here with the same value, except the
+    # reference's N_TM6144 = 6140 typo which is corrected to 6144 (documented in the header)
+    for mname, val in kats["header_macros"].items():
+        key = mname.replace("LABRADOR_LDPC_", "")
+        if mname == "LABRADOR_LDPC_N_TM6144":
+            assert val == 6140 and int(out["N_TM6144"]) == 6144
+        else:
+            assert int(out[key]) == val, mname
+
+
+def test_example_c_builds_against_header(tmp_path):
+    # the reference's capi/examples/example.c pattern: static buffers sized by the macros
+    src = tmp_path / "ex.c"
+    src.write_text('''
+#include <stdint.h>
+#include <stdbool.h>
+#include "labrador_ldpc.h"
+#define CODE TC128
+uint8_t message[LABRADOR_LDPC_K(CODE)/8];
+uint8_t codeword[LABRADOR_LDPC_N(CODE)/8];
+float llrs[LABRADOR_LDPC_N(CODE)];
+float working[LABRADOR_LDPC_MS_WORKING_LEN(CODE)];
+uint8_t working_u8[LABRADOR_LDPC_MS_WORKING_U8_LEN(CODE)];
+uint8_t output[LABRADOR_LDPC_OUTPUT_LEN(CODE)];
+int main(void) {
+    enum labrador_ldpc_code code = LABRADOR_LDPC_CODE(CODE);
+    if (labrador_ldpc_code_n(code) != 128) return 1;
+    if (sizeof(working)/sizeof(working[0]) != labrador_ldpc_ms_working_len(code)) return 2;
+    if (sizeof(output) != labrador_ldpc_output_len(code)) return 3;
+    return 0;
+}''')
+    import labrador_ldpc_b200 as L
+    libdir = os.path.dirname(L._LIB_PATH)
+    exe = tmp_path / "ex"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-llabrador_ldpc", "-Wl,-rpath," + libdir])
+    assert subprocess.call([str(exe)]) == 0
+
+
+def test_argument_validation_needs_no_gpu(ldpc):
+    L = ldpc.lib
+    buf = np.zeros(64, np.uint8)
+    p = buf.ctypes.data
+    assert L.labrador_ldpc_decode_ms_i8_batch(9, p, p, 1, 10, p, None) == -1      # bad code
+    assert L.labrador_ldpc_decode_ms_i8_batch(0, None, p, 1, 10, p, None) == -2   # null pointer
+    assert L.labrador_ldpc_decode_ms_i8_batch(0, None, None, 0, 10, None, None) == 0  # empty batch is a no-op
+    assert L.labrador_ldpc_decode_bf_batch(-1, p, p, 1, 10, p, None) == -1
+    assert L.labrador_ldpc_copy_encode_batch(0, None, p, 1) == -2
+    assert L.labrador_ldpc_decode_ms_batch_async(0, 7, p, p, 1, 10, p, None, None) == -5   # bad llr type
+    assert b"llr_type" in L.labrador_ldpc_last_error()
+
+
+def test_python_mirror_length_asserts(ldpc):
+    # the reference asserts every buffer length (src/decoder.rs:356-359, src/encoder.rs:296,312-313)
+    c = ldpc.LDPCCode.TC128
+    with pytest.raises(ValueError):
+        c.decode_ms(np.zeros(127, np.int8), np.zeros(16, np.uint8))
+    with pytest.raises(ValueError):
+        c.decode_ms(np.zeros(128, np.int8), np.zeros(15, np.uint8))
+    with pytest.raises(ValueError):
+        c.decode_ms(np.zeros(128, np.int8), np.zeros(16, np.uint8), working=np.zeros(3, np.int8))
+    with pytest.raises(ValueError):
+        c.decode_bf(np.zeros(15, np.uint8), np.zeros(16, np.uint8))
+    with pytest.raises(ValueError):
+        c.copy_encode(np.zeros(7, np.uint8), np.zeros(16, np.uint8))
+    with pytest.raises(ValueError):
+        c.encode(np.zeros(15, np.uint8))
+
+
+def test_no_cpu_fallback_without_gpu(ldpc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    c = ldpc.LDPCCode.TC128
+    with pytest.raises(ldpc.LdpcError):
+        c.decode_ms_batch(np.zeros((2, 128), np.int8), 10)
+    with pytest.raises(ldpc.LdpcError):
+        c.copy_encode_batch(np.zeros((2, 8), np.uint8))
+
+
+def test_product_never_touches_oracle():
+    pkg = os.path.join(ROOT, "labrador_ldpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text.replace(
+                    "oracle/ccsds_tables.h", ""), (dirpath, f)

@@ -1,0 +1,388 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Integer LLR types must match the oracle exactly (decoded bytes, success flag, iteration
+count) on every frame; float types must give identical hard decisions on >= 99.99 % of
+frames (north_star) -- tolerance written in `assert_float_parity`.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from frames import hard_frames, make_frames
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["TC128", "TC256", "TC512", "TM1280", "TM1536", "TM2048", "TM5120", "TM6144", "TM8192"]
+CODES = list(range(9))
+# Eb/N0 per code where decoding mostly, but not always, succeeds (mix of iteration counts)
+EBN0 = {0: 3.0, 1: 3.0, 2: 2.5, 3: 3.6, 4: 2.6, 5: 1.8, 6: 3.4, 7: 2.4, 8: 1.6}
+
+
+def assert_exact(got, want, what):
+    out_g, ok_g, it_g = got
+    out_w, ok_w, it_w = want
+    assert np.array_equal(np.asarray(ok_g).astype(bool), np.asarray(ok_w).astype(bool)), what + ": success flags differ"
+    assert np.array_equal(np.asarray(it_g).astype(np.int64), np.asarray(it_w).astype(np.int64)), what + ": iteration counts differ"
+    assert np.array_equal(np.asarray(out_g), np.asarray(out_w)), what + ": decoded bytes differ"
+
+
+def assert_float_parity(got, want, what, min_frac=0.9999):
+    out_g, ok_g, it_g = got
+    out_w, ok_w, it_w = want
+    same = (np.asarray(out_g) == np.asarray(out_w)).all(axis=1)
+    same &= np.asarray(ok_g).astype(bool) == np.asarray(ok_w).astype(bool)
+    same &= np.asarray(it_g).astype(np.int64) == np.asarray(it_w).astype(np.int64)
+    assert same.mean() >= min_frac, "%s: only %.5f of frames identical" % (what, same.mean())
+
+
+@pytest.mark.parametrize("code", CODES)
+@pytest.mark.parametrize("ty", ["i8", "i16", "i32", "f32", "f64"])
+def test_reference_decode_ms_vector(ldpc, oracle, code, ty):
+    # reference src/decoder.rs:671-699 for every LLR type, single-codeword C entry point semantics
+    c = ldpc.LDPCCode(code)
+    data = (np.arange(c.k() // 8) % 256).astype(np.uint8)
+    cw = np.zeros(c.n() // 8, np.uint8)
+    c.copy_encode(data, cw)
+    assert np.array_equal(cw, oracle.copy_encode(code, data))
+    rx = cw.copy()
+    rx[0] ^= (1 << 7) | (1 << 5) | (1 << 3)
+    llrs = np.zeros(c.n(), ldpc._NP_OF[ty])
+    c.hard_to_llrs(rx, llrs)
+    assert np.array_equal(llrs, oracle.hard_to_llrs(code, rx, ty))
+    out = np.zeros(c.output_len(), np.uint8)
+    ok, iters = c.decode_ms(llrs, out, maxiters=50)
+    ok_w, it_w, out_w = oracle.decode_ms(code, llrs, 50)
+    assert ok and ok_w and iters == it_w
+    assert np.array_equal(out, out_w)
+    assert np.array_equal(out[: cw.size], cw)
+
+
+@pytest.mark.parametrize("code", CODES)
+def test_reference_decode_bf_vector(ldpc, oracle, code):
+    # reference src/decoder.rs:647-670 and the doc-test src/lib.rs:21-50
+    c = ldpc.LDPCCode(code)
+    data = (np.arange(c.k() // 8) % 256).astype(np.uint8)
+    cw = oracle.copy_encode(code, data)
+    for flip in (0xA8, 0x55):
+        rx = cw.copy()
+        rx[0] ^= flip
+        out = np.zeros(c.output_len(), np.uint8)
+        ok, iters = c.decode_bf(rx, out, maxiters=50)
+        ok_w, it_w, out_w = oracle.decode_bf(code, rx, 50)
+        assert (ok, iters) == (ok_w, it_w)
+        assert np.array_equal(out, out_w)
+        if flip == 0xA8:
+            assert ok and np.array_equal(out[: cw.size], cw)
+
+
+def test_reference_signature_c_functions(ldpc, oracle, kats):
+    """The 21 reference entry points called exactly as capi/examples/example.c does."""
+    L = ldpc.lib
+    code = 0
+    msg = np.arange(8, dtype=np.uint8)
+    cw = np.zeros(16, np.uint8)
+    L.labrador_ldpc_copy_encode(code, msg.ctypes.data, cw.ctypes.data)
+    assert cw.tolist() == kats["doctest_tc128_codeword"]
+    cw2 = np.zeros(16, np.uint8)
+    cw2[:8] = msg
+    L.labrador_ldpc_encode(code, cw2.ctypes.data)
+    assert np.array_equal(cw, cw2)
+    # unaligned codeword pointer (the reference takes its u8 path, capi/src/lib.rs:27-33)
+    raw = np.zeros(17, np.uint8)
+    raw[1:9] = msg
+    L.labrador_ldpc_encode(code, raw.ctypes.data + 1)
+    assert np.array_equal(raw[1:], cw)
+    rx = cw.copy()
+    rx[7] = 0          # example.c erases the last byte of user data
+    llrs = np.zeros(128, np.float32)
+    L.labrador_ldpc_hard_to_llrs_f32(code, rx.ctypes.data, llrs.ctypes.data)
+    assert np.array_equal(llrs, oracle.hard_to_llrs(code, rx, "f32"))
+    out = np.zeros(16, np.uint8)
+    working = np.zeros(L.labrador_ldpc_ms_working_len(code), np.float32)
+    working_u8 = np.zeros(L.labrador_ldpc_ms_working_u8_len(code), np.uint8)
+    iters = ctypes.c_size_t(99)
+    ok = L.labrador_ldpc_decode_ms_f32(code, llrs.ctypes.data, out.ctypes.data, working.ctypes.data,
+                                       working_u8.ctypes.data, 200, ctypes.addressof(iters))
+    ok_w, it_w, out_w = oracle.decode_ms(code, llrs, 200)
+    assert bool(ok) == ok_w and iters.value == it_w and np.array_equal(out, out_w)
+    # iters_run may be NULL (capi/src/lib.rs:77,91)
+    ok = L.labrador_ldpc_decode_ms_f32(code, llrs.ctypes.data, out.ctypes.data, working.ctypes.data,
+                                       working_u8.ctypes.data, 200, None)
+    assert bool(ok) == ok_w
+    hard = np.zeros(16, np.uint8)
+    L.labrador_ldpc_llrs_to_hard_f32(code, llrs.ctypes.data, hard.ctypes.data)
+    assert np.array_equal(hard, rx)
+    bfw = np.zeros(L.labrador_ldpc_bf_working_len(code), np.uint8)
+    rx2 = cw.copy()
+    rx2[0] ^= 0x55
+    ok = L.labrador_ldpc_decode_bf(code, rx2.ctypes.data, out.ctypes.data, bfw.ctypes.data, 20, ctypes.addressof(iters))
+    ok_w, it_w, out_w = oracle.decode_bf(code, rx2, 20)
+    assert bool(ok) == ok_w and iters.value == it_w and np.array_equal(out, out_w)
+    for t, npdt in (("i8", np.int8), ("i16", np.int16), ("f64", np.float64)):
+        l2 = np.zeros(128, npdt)
+        getattr(L, "labrador_ldpc_hard_to_llrs_" + t)(code, rx.ctypes.data, l2.ctypes.data)
+        assert np.array_equal(l2, oracle.hard_to_llrs(code, rx, t))
+        h2 = np.zeros(16, np.uint8)
+        getattr(L, "labrador_ldpc_llrs_to_hard_" + t)(code, l2.ctypes.data, h2.ctypes.data)
+        assert np.array_equal(h2, rx)
+
+
+def test_converter_kat(ldpc, kats):
+    # reference src/decoder.rs:553-605
+    c = ldpc.LDPCCode.TC128
+    hard = np.array(kats["convert_hard"], np.uint8)
+    want = np.array(kats["convert_llrs"], np.float32)
+    llrs = np.zeros(128, np.float32)
+    c.hard_to_llrs(hard, llrs)
+    assert np.array_equal(llrs, want)
+    back = np.zeros(16, np.uint8)
+    c.llrs_to_hard(llrs, back)
+    assert np.array_equal(back, hard)
+    z = np.full(128, -0.0, np.float32)     # -0.0 is a 0 bit
+    c.llrs_to_hard(z, back)
+    assert not back.any()
+
+
+@pytest.mark.parametrize("code", CODES)
+def test_encode_kat_and_random(ldpc, oracle, kats, code):
+    # reference src/encoder.rs:361-527 known answers, then random data against the oracle
+    c = ldpc.LDPCCode(code)
+    data = (np.arange(c.k() // 8) % 256).astype(np.uint8)
+    cw = np.zeros(c.n() // 8, np.uint8)
+    c.copy_encode(data, cw)
+    assert cw[data.size:].tolist() == kats["encode_parity"][NAMES[code]]
+    rng = np.random.default_rng(code)
+    batch = 257
+    d = rng.integers(0, 256, (batch, c.k() // 8), dtype=np.uint8)
+    d[0] = 0
+    d[1] = 0xFF
+    want = oracle.copy_encode_batch(code, d, nthreads=4)
+    got = c.copy_encode_batch(d)
+    assert np.array_equal(got, want)
+    inplace = np.zeros_like(want)
+    inplace[:, : c.k() // 8] = d
+    c.encode_batch(inplace)
+    assert np.array_equal(inplace, want)
+    # linearity over GF(2): enc(a ^ b) == enc(a) ^ enc(b)
+    x = c.copy_encode_batch(d[2:3] ^ d[3:4])
+    assert np.array_equal(x[0], want[2] ^ want[3])
+
+
+@pytest.mark.parametrize("code", CODES)
+def test_decode_ms_i8_awgn_exact(ldpc, oracle, code):
+    c = ldpc.LDPCCode(code)
+    batch = 384 if code < 6 else 160
+    _, _, llrs = make_frames(oracle, code, batch, EBN0[code], seed=100 + code, ty="i8")
+    want = oracle.decode_ms_batch(code, llrs, 100, nthreads=8)
+    got = c.decode_ms_batch(llrs, 100)
+    assert_exact(got, want, NAMES[code] + " i8")
+    assert 0 < want[1].sum(), "test vector should contain successes"
+
+
+@pytest.mark.parametrize("code", [0, 2, 3, 5, 8])
+@pytest.mark.parametrize("ty", ["i16", "i32"])
+def test_decode_ms_wide_int_awgn_exact(ldpc, oracle, code, ty):
+    c = ldpc.LDPCCode(code)
+    batch = 128 if code < 6 else 64
+    _, _, llrs = make_frames(oracle, code, batch, EBN0[code], seed=200 + code, ty=ty)
+    want = oracle.decode_ms_batch(code, llrs, 60, nthreads=8)
+    got = c.decode_ms_batch(llrs, 60)
+    assert_exact(got, want, "%s %s" % (NAMES[code], ty))
+
+
+@pytest.mark.parametrize("code", [0, 1, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("ty", ["f32", "f64"])
+def test_decode_ms_float_awgn(ldpc, oracle, code, ty):
+    c = ldpc.LDPCCode(code)
+    batch = 128 if code < 6 else 48
+    _, _, llrs = make_frames(oracle, code, batch, EBN0[code], seed=300 + code, ty=ty)
+    want = oracle.decode_ms_batch(code, llrs, 60, nthreads=8)
+    got = c.decode_ms_batch(llrs, 60)
+    assert_float_parity(got, want, "%s %s" % (NAMES[code], ty))
+
+
+@pytest.mark.parametrize("code", CODES)
+def test_decode_ms_i8_saturation_stress(ldpc, oracle, code):
+    """Full-range random LLRs: decoding fails, every saturating add/sub/abs corner is hit
+    (incl. -128), and the output is the hard decision of the LAST marginals -- so the
+    whole message state must match the oracle after `maxiters` iterations."""
+    c = ldpc.LDPCCode(code)
+    rng = np.random.default_rng(400 + code)
+    batch = 64 if code < 6 else 24
+    llrs = rng.integers(-128, 128, (batch, c.n())).astype(np.int8)
+    llrs[0, :] = -128
+    llrs[1, :] = 127
+    llrs[2, ::2] = -128
+    for maxiters in (1, 2, 9):
+        want = oracle.decode_ms_batch(code, llrs, maxiters, nthreads=8)
+        got = c.decode_ms_batch(llrs, maxiters)
+        assert_exact(got, want, "%s i8 stress maxiters=%d" % (NAMES[code], maxiters))
+    # large-magnitude but decodable: saturation on the way to success
+    _, _, soft = make_frames(oracle, code, batch, EBN0[code] + 1.0, seed=450 + code, ty="f64")
+    big = np.clip(np.rint(24.0 * soft), -127, 127).astype(np.int8)
+    want = oracle.decode_ms_batch(code, big, 40, nthreads=8)
+    got = c.decode_ms_batch(big, 40)
+    assert_exact(got, want, NAMES[code] + " i8 big-llr")
+
+
+@pytest.mark.parametrize("code", [5, 8])
+def test_decode_ms_i16_saturation_stress(ldpc, oracle, code):
+    c = ldpc.LDPCCode(code)
+    rng = np.random.default_rng(500 + code)
+    llrs = rng.integers(-32768, 32768, (16, c.n())).astype(np.int16)
+    want = oracle.decode_ms_batch(code, llrs, 6, nthreads=8)
+    got = c.decode_ms_batch(llrs, 6)
+    assert_exact(got, want, NAMES[code] + " i16 stress")
+
+
+def test_decode_ms_maxiters_edge_cases(ldpc, oracle):
+    for code in (0, 5):
+        c = ldpc.LDPCCode(code)
+        _, _, llrs = make_frames(oracle, code, 8, 4.0, seed=7, ty="i8")
+        for maxiters in (0, 1):
+            want = oracle.decode_ms_batch(code, llrs, maxiters)
+            got = c.decode_ms_batch(llrs, maxiters)
+            assert_exact(got, want, "maxiters=%d" % maxiters)
+        out, ok, it = c.decode_ms_batch(llrs, 0)
+        assert not out.any() and not ok.any() and not it.any()
+        # clean codeword, +-1 LLRs: (true, 0) for TC, (true, 1) for TM
+        cw = oracle.copy_encode(code, (np.arange(c.k() // 8) % 256).astype(np.uint8))
+        l1 = oracle.hard_to_llrs(code, cw, "i8")
+        out = np.zeros(c.output_len(), np.uint8)
+        assert c.decode_ms(l1, out, maxiters=50) == oracle.decode_ms(code, l1, 50)[:2]
+
+
+@pytest.mark.parametrize("code", CODES)
+def test_decode_bf_random_errors(ldpc, oracle, code):
+    c = ldpc.LDPCCode(code)
+    for flips in (0, 1, 3, 7, 20):
+        _, _, rx = hard_frames(oracle, code, 48, flips, seed=600 + code + flips)
+        want = oracle.decode_bf_batch(code, rx, 30, nthreads=8)
+        got = c.decode_bf_batch(rx, 30)
+        assert_exact(got, want, "%s bf flips=%d" % (NAMES[code], flips))
+    for maxiters in (0, 1):
+        want = oracle.decode_bf_batch(code, rx, maxiters)
+        got = c.decode_bf_batch(rx, maxiters)
+        assert_exact(got, want, "%s bf maxiters=%d" % (NAMES[code], maxiters))
+
+
+@pytest.mark.parametrize("code", [c for c in CODES if c >= 3])
+def test_erasure_prepass_matches_min_sum(ldpc, oracle, code):
+    # reference src/decoder.rs:607-645: on a clean codeword the punctured bits recovered by
+    # the erasure pre-pass of decode_bf equal those recovered by decode_ms
+    c = ldpc.LDPCCode(code)
+    cw = oracle.copy_encode(code, (np.arange(c.k() // 8) % 256).astype(np.uint8))
+    out_bf = np.zeros(c.output_len(), np.uint8)
+    ok, iters = c.decode_bf(cw, out_bf, maxiters=50)
+    out_ms = np.zeros(c.output_len(), np.uint8)
+    ok2, _ = c.decode_ms(oracle.hard_to_llrs(code, cw, "i8"), out_ms, maxiters=50)
+    assert ok and ok2 and iters == 0
+    assert np.array_equal(out_bf, out_ms)
+
+
+@pytest.mark.parametrize("ty", ["i8", "i16", "i32", "f32", "f64"])
+def test_converters_random(ldpc, oracle, ty):
+    rng = np.random.default_rng(9)
+    for code in (0, 4, 8):
+        c = ldpc.LDPCCode(code)
+        hard = rng.integers(0, 256, (37, c.n() // 8), dtype=np.uint8)
+        llrs = c.hard_to_llrs_batch(hard, ty)
+        for f in (0, 36):
+            assert np.array_equal(llrs[f], oracle.hard_to_llrs(code, hard[f], ty))
+        assert np.array_equal(c.llrs_to_hard_batch(llrs), hard)
+        noisy = (rng.standard_normal((37, c.n())) * 50).astype(ldpc._NP_OF[ty])
+        got = c.llrs_to_hard_batch(noisy)
+        for f in (0, 18, 36):
+            assert np.array_equal(got[f], oracle.llrs_to_hard(code, noisy[f], ty))
+
+
+def test_device_pointers_pinned_and_chunking(ldpc, oracle):
+    """Same frames through: pageable host, pinned host, device tensors, and a host batch
+    forced through many pipeline chunks -- all must agree with the oracle."""
+    import torch
+    code = 5
+    c = ldpc.LDPCCode(code)
+    _, _, llrs = make_frames(oracle, code, 700, EBN0[code], seed=11, ty="i8")
+    want = oracle.decode_ms_batch(code, llrs, 50, nthreads=8)
+    assert_exact(c.decode_ms_batch(llrs, 50), want, "pageable")
+    t_pinned = torch.from_numpy(llrs).pin_memory()
+    got = c.decode_ms_batch(t_pinned, 50)
+    assert_exact([g.numpy() for g in got], want, "pinned")
+    t_dev = torch.from_numpy(llrs).cuda()
+    got = c.decode_ms_batch(t_dev, 50)
+    torch.cuda.synchronize()
+    assert_exact([g.cpu().numpy() for g in got], want, "device")
+    # odd offsets / unaligned host views
+    raw = np.zeros(llrs.size + 3, np.int8)
+    raw[3:] = llrs.ravel()
+    got = c.decode_ms_batch(raw[3:].reshape(llrs.shape), 50)
+    assert_exact(got, want, "unaligned")
+    # mixed pointer kinds are rejected
+    with pytest.raises(ldpc.LdpcError):
+        c.decode_ms_batch(t_dev, 50, output=np.zeros((700, c.output_len()), np.uint8))
+
+
+def test_many_chunks_pipeline(oracle):
+    """Run in a subprocess with a 1 MiB chunk target so a modest batch crosses many
+    pipeline chunks (buffer reuse across the 3 slots)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle"); sys.path.insert(0, %r + "/tests")
+import labrador_ldpc_b200 as L, pyoracle
+from frames import make_frames
+o = pyoracle.Oracle()
+code = 2
+_, _, llrs = make_frames(o, code, 9001, 3.0, seed=3, ty="i8")
+want = o.decode_ms_batch(code, llrs, 20, nthreads=8)
+got = L.LDPCCode(code).decode_ms_batch(llrs, 20)
+assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want))
+print("OK")
+''' % (root, root, root)
+    env = dict(os.environ, LABRADOR_LDPC_CHUNK_MB="1")
+    out = subprocess.check_output([sys.executable, "-c", script], env=env, text=True)
+    assert "OK" in out
+
+
+def test_full_size_properties_tm8192(ldpc, oracle):
+    """BASELINE config 3 shape at a size the GPU handles in seconds: properties that need no
+    oracle (decoded data == transmitted data on success, re-encoding the decoded data gives
+    the decoded codeword, iteration counts in range), plus exact parity on a prefix sample."""
+    import torch
+    code = 8
+    c = ldpc.LDPCCode(code)
+    batch = 16384
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    data = torch.randint(0, 256, (batch, c.k() // 8), dtype=torch.uint8, device="cuda", generator=g)
+    cw = c.copy_encode_batch(data)
+    bits = ((cw.unsqueeze(-1) >> torch.arange(7, -1, -1, device="cuda", dtype=torch.uint8)) & 1).reshape(batch, -1)
+    sigma2 = 1.0 / (2.0 * 0.5 * 10.0 ** (2.0 / 10.0))
+    y = (1.0 - 2.0 * bits.float()) + (sigma2 ** 0.5) * torch.randn(bits.shape, device="cuda", generator=g)
+    llrs = torch.clamp(torch.round(4.0 * 2.0 * y / sigma2), -31, 31).to(torch.int8).contiguous()
+    out, ok, iters = c.decode_ms_batch(llrs, 100)
+    torch.cuda.synchronize()
+    okb = ok.bool()
+    assert okb.float().mean().item() > 0.99
+    assert torch.equal(out[okb][:, : c.k() // 8], data[okb])
+    assert torch.equal(out[okb][:, : c.n() // 8], cw[okb])
+    reenc = c.copy_encode_batch(out[:, : c.k() // 8].contiguous())
+    assert torch.equal(reenc[okb], out[okb][:, : c.n() // 8])
+    assert int(iters[okb].max()) < 100 and bool((iters[~okb] == 100).all())
+    # exact parity with the oracle on a prefix of the very same LLR bytes
+    sample = llrs[:96].cpu().numpy()
+    want = oracle.decode_ms_batch(code, sample, 100, nthreads=8)
+    assert_exact((out[:96].cpu().numpy(), ok[:96].cpu().numpy(), iters[:96].cpu().numpy()), want, "prefix sample")
+
+
+def test_launch_counter_and_kernel_names(ldpc):
+    before = ldpc.kernel_launch_count()
+    c = ldpc.LDPCCode.TC128
+    c.decode_ms_batch(np.zeros((4, 128), np.int8), 3)
+    assert ldpc.kernel_launch_count() > before
+    for ty in ("i8", "i16", "i32", "f32", "f64"):
+        assert c.decode_ms_kernel_name(ty).startswith("ms_")
