@@ -1,0 +1,476 @@
+// Specialised min-sum decoder for the TM codes with i8 LLRs (the headline path).
+//
+// Replaces LDPCCode::decode_ms::<i8> (reference src/decoder.rs:347-475) for
+// TM1536/TM2048/TM5120/TM6144/TM8192; results (decoded bytes, success flag,
+// iteration count) are bit-identical to the reference's flooding schedule.
+//
+// One CTA decodes one codeword at a time (persistent CTAs pull frame indices
+// from an atomic counter).  All arithmetic is done on two 16-bit lanes per
+// 32-bit register with the native packed instructions of sm_100a
+// (VIADDMNMX.S16x2.RELU, VIMNMX.S16x2, VIADD.16x2, PRMT, LOP3).
+//
+// Lane pairing.  Inside every quarter (Q = M/4 elements) of an MxM block the
+// elements x and x + S (S = Q/2) share a register.  The pi_k permutation of a
+// block is "quarter q -> (theta+q) mod 4, offset x -> (phi_q + x) mod Q"
+// (reference src/codes/mod.rs:312-322), so it maps lane pairs to lane pairs --
+// at most the two lanes swap.  Word slot = q*S + w, w in [0,S).  Thread t owns
+// word slot t of EVERY prototype column (variable side) and EVERY prototype
+// row (check side); M/2 threads per CTA.
+//
+// Messages.  Identity blocks connect check slot t with variable slot t of the
+// same thread, so their messages never leave the thread's registers.  Only the
+// permutation blocks go through shared memory: one 32-bit word per lane pair,
+// stored in check order (own slot for the check side, permuted address +
+// optional lane swap for the variable side; consecutive threads hit
+// consecutive words, so there are no bank conflicts).
+//
+// Representations (all exact, see DESIGN.md for the derivations):
+//   variable side: VA = marginal + 128 in [0,255]; saturating_add(va, u) is one
+//       VIADDMNMX.RELU: max(min(VA + u, 255), 0)                     (:408)
+//   variable -> check: C = 127 - clamp(va - u, -127, 127) in [0,254], one
+//       VIADDMNMX.RELU on VAn = 255 - VA.  -128 and -127 are interchangeable
+//       because v is only ever used through saturating_abs, sign and == 0.
+//   check side: sign = bit 7 of C, |v| + 127 = max(C, 254 - C).  The
+//       self-correction rule (:422-426) needs only the sign class of the
+//       previous v, kept as Cc_old: kill = bit7((C ^ Cc_old) & (C ^ (Cc_old+1))).
+//   check -> variable: u_j = +-(min_{k != j} |v_k|) by prefix/suffix minima
+//       (equal to the reference's min1/min2 selection, :391-395), sign
+//       = parity of the other edges' signs (:398-405), as two's complement.
+// The per-iteration parity test (:445-453) runs bit-packed: warp ballots pack
+// the marginals' hard bits, the syndrome is XORs of funnel-shifted words.
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "runtime.h"
+
+namespace ldpc {
+namespace {
+
+struct Blk { int row, col, isp; };
+
+template <int RATE> struct Proto;
+
+// Block lists in the reference iterator's order; checked against
+// the run-time expansion of the prototype tables before the kernel is ever used.
+template <> struct Proto<0> {   // rate 1/2: TM2048 (M=512), TM8192 (M=2048)
+    static constexpr int NB = 15, NCOL = 5, NROW = 3;
+    __host__ __device__ static constexpr Blk blk(int b) {
+        constexpr Blk t[NB] = {{0, 2, 0}, {0, 4, 0}, {0, 4, 1}, {1, 0, 0}, {1, 1, 0}, {1, 3, 0}, {1, 4, 1}, {1, 4, 1},
+                               {1, 4, 1}, {2, 0, 0}, {2, 1, 1}, {2, 1, 1}, {2, 3, 1}, {2, 3, 1}, {2, 4, 0}};
+        return t[b];
+    }
+};
+template <> struct Proto<1> {   // rate 2/3: TM1536 (M=256), TM6144 (M=1024)
+    static constexpr int NB = 23, NCOL = 7, NROW = 3;
+    __host__ __device__ static constexpr Blk blk(int b) {
+        constexpr Blk t[NB] = {{0, 4, 0}, {0, 6, 0}, {0, 6, 1}, {1, 0, 1}, {1, 0, 1}, {1, 0, 1}, {1, 1, 0}, {1, 2, 0},
+                               {1, 3, 0}, {1, 5, 0}, {1, 6, 1}, {1, 6, 1}, {1, 6, 1}, {2, 0, 0}, {2, 1, 1}, {2, 1, 1},
+                               {2, 1, 1}, {2, 2, 0}, {2, 3, 1}, {2, 3, 1}, {2, 5, 1}, {2, 5, 1}, {2, 6, 0}};
+        return t[b];
+    }
+};
+template <> struct Proto<2> {   // rate 4/5: TM5120 (M=512)  (TM1280, M=128, stays on the generic kernel)
+    static constexpr int NB = 39, NCOL = 11, NROW = 3;
+    __host__ __device__ static constexpr Blk blk(int b) {
+        constexpr Blk t[NB] = {{0, 8, 0},  {0, 10, 0}, {0, 10, 1}, {1, 0, 1},  {1, 0, 1},  {1, 0, 1},  {1, 1, 0},
+                               {1, 2, 1},  {1, 2, 1},  {1, 2, 1},  {1, 3, 0},  {1, 4, 1},  {1, 4, 1},  {1, 4, 1},
+                               {1, 5, 0},  {1, 6, 0},  {1, 7, 0},  {1, 9, 0},  {1, 10, 1}, {1, 10, 1}, {1, 10, 1},
+                               {2, 0, 0},  {2, 1, 1},  {2, 1, 1},  {2, 1, 1},  {2, 2, 0},  {2, 3, 1},  {2, 3, 1},
+                               {2, 3, 1},  {2, 4, 0},  {2, 5, 1},  {2, 5, 1},  {2, 5, 1},  {2, 6, 0},  {2, 7, 1},
+                               {2, 7, 1},  {2, 9, 1},  {2, 9, 1},  {2, 10, 0}};
+        return t[b];
+    }
+};
+
+template <class P> __host__ __device__ constexpr int count_p(int upto) {
+    int c = 0;
+    for (int b = 0; b < upto; b++) c += P::blk(b).isp;
+    return c;
+}
+template <class P> __host__ __device__ constexpr int count_i(int upto) { return upto - count_p<P>(upto); }
+template <class P> __host__ __device__ constexpr int row_degree(int r) {
+    int c = 0;
+    for (int b = 0; b < P::NB; b++) c += P::blk(b).row == r;
+    return c;
+}
+template <class P> __host__ __device__ constexpr int col_degree(int col) {
+    int c = 0;
+    for (int b = 0; b < P::NB; b++) c += P::blk(b).col == col;
+    return c;
+}
+// index (0-based) of block b among the blocks of its row / column
+template <class P> __host__ __device__ constexpr int pos_in_row(int b) {
+    int c = 0;
+    for (int i = 0; i < b; i++) c += P::blk(i).row == P::blk(b).row;
+    return c;
+}
+template <class P> __host__ __device__ constexpr int pos_in_col(int b) {
+    int c = 0;
+    for (int i = 0; i < b; i++) c += P::blk(i).col == P::blk(b).col;
+    return c;
+}
+
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// theta / phi of every block in block order (only permutation blocks are read)
+struct TmParams {
+    uint8_t theta[40];
+    uint16_t phi[40][4];
+};
+
+__device__ __forceinline__ uint32_t prmt_sign7(uint32_t x) {
+    // bytes 0,1 <- sign of byte 0; bytes 2,3 <- sign of byte 2 (bit 7 of each 16-bit lane -> lane mask)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xaa88;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t lane_rot(uint32_t x, uint32_t sh) { return __funnelshift_l(x, x, sh); }
+
+constexpr int kMaxDeg = 18;
+
+// Minimum over "all the other edges" for every edge of one check word: prefix/suffix minima.
+template <int DC> __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
+    uint32_t suf[kMaxDeg];
+    suf[DC - 1] = a[DC - 1];
+#pragma unroll
+    for (int k = DC - 2; k >= 1; k--) suf[k] = __vminu2(a[k], suf[k + 1]);
+    uint32_t pre = a[0];
+    mu[0] = suf[1];
+#pragma unroll
+    for (int k = 1; k < DC - 1; k++) {
+        mu[k] = __vminu2(pre, suf[k + 1]);
+        pre = __vminu2(pre, a[k]);
+    }
+    mu[DC - 1] = pre;
+}
+
+template <int RATE, int M, int WPT>
+__global__ void __launch_bounds__(M / 2 / WPT)
+decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
+                       unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
+                       uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+    typedef Proto<RATE> P;
+    constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
+    constexpr int NP = count_p<P>(NB), NI = NB - NP;
+    constexpr int Q = M / 4, S = Q / 2, NT = M / 2 / WPT;
+    constexpr int NV = NCOL * M, N = (NCOL - 1) * M, NC = NROW * M;
+    constexpr int HBW = NV / 32;           // hard-decision words
+    constexpr int SYW = NC / 32;           // syndrome words
+    static_assert(S >= 32 && S % 32 == 0, "lane pairing needs at least one warp per half quarter");
+    static_assert(SYW <= NT, "one thread per syndrome word");
+
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    uint32_t *msg = smem_u32;                       // [NP][M/2] permutation-block messages, check order
+    uint32_t *hb = msg + NP * (M / 2);              // [HBW] packed hard decisions, bit i of word j = variable 32j+i
+    __shared__ unsigned long long s_frame;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    // per-thread constants: permuted word address + lane swap of every permutation block
+    uint32_t paddr[NP > 0 ? NP : 1][WPT], pswp[NP > 0 ? NP : 1][WPT];
+#pragma unroll
+    for (int wi = 0; wi < WPT; wi++) {
+        const int wd = tid + wi * NT;
+        const int qv = wd / S, wv = wd % S;
+        static_for<0, NB>([&](auto bi) {
+            constexpr int b = decltype(bi)::value;
+            if constexpr (P::blk(b).isp) {
+                constexpr int ps = count_p<P>(b);
+                const int q = (qv - (int)prm.theta[b]) & 3;
+                const int phi = prm.phi[b][q];
+                const int phi_lo = phi % S, phi_hi = phi / S;
+                const int borrow = wv < phi_lo ? 1 : 0;
+                const int w = (wv - phi_lo) & (S - 1);
+                paddr[ps][wi] = (uint32_t)(ps * (M / 2) + q * S + w);
+                pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 16u : 0u;
+            }
+        });
+    }
+
+    for (;;) {
+        if (tid == 0) s_frame = atomicAdd(counter, 1ull);
+        __syncthreads();
+        const unsigned long long frame = s_frame;
+        if (frame >= batch) break;
+        const int8_t *llr = llrs_all + frame * (unsigned long long)N;
+
+        // ---- per-frame state: everything zero, every call (:368, :374) ----
+        uint32_t Lb[NCOL][WPT];       // channel LLR + 128 (punctured column: 128)
+        uint32_t idm[NI > 0 ? NI : 1][WPT];   // identity-block messages (u after the check phase, C after the variable phase)
+        uint32_t cc[NB][WPT];         // corrected C of the previous iteration (sign class of the old v)
+#pragma unroll
+        for (int wi = 0; wi < WPT; wi++) {
+            const int wd = tid + wi * NT;
+            const int e0 = (wd / S) * Q + (wd % S);
+#pragma unroll
+            for (int c = 0; c < NCOL; c++) {
+                if (c < NCOL - 1) {
+                    const int l0 = llr[c * M + e0], l1 = llr[c * M + e0 + S];
+                    Lb[c][wi] = (uint32_t)(l0 + 128) | ((uint32_t)(l1 + 128) << 16);
+                } else {
+                    Lb[c][wi] = 0x00800080u;                                      // :383
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NI; i++) idm[i][wi] = 0;
+#pragma unroll
+            for (int b = 0; b < NB; b++) cc[b][wi] = 0x007f007fu;
+#pragma unroll
+            for (int p = 0; p < NP; p++) msg[p * (M / 2) + wd] = 0;
+        }
+        for (int i = tid; i < HBW; i += NT) hb[i] = 0;
+        __syncthreads();
+
+        unsigned iters_run = max_iters;
+        bool ok = false;
+        for (unsigned iter = 0; iter < max_iters; iter++) {
+            // ================= variable phase (:382-411 and :421) =================
+#pragma unroll
+            for (int wi = 0; wi < WPT; wi++) {
+                const int wd = tid + wi * NT;
+                static_for<0, NCOL>([&](auto ci) {
+                    constexpr int c = decltype(ci)::value;
+                    uint32_t va = Lb[c][wi];
+                    uint32_t ub[6];
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).col == c) {
+                            constexpr int k = pos_in_col<P>(b);
+                            uint32_t u;
+                            if constexpr (P::blk(b).isp) {
+                                constexpr int ps = count_p<P>(b);
+                                u = lane_rot(msg[paddr[ps][wi]], pswp[ps][wi]);
+                            } else {
+                                u = idm[count_i<P>(b)][wi];
+                            }
+                            ub[k] = u;
+                            va = __viaddmin_s16x2_relu(va, u, 0x00ff00ffu);      // saturating_add, ascending idx
+                        }
+                    });
+                    // hard decisions of the marginals: va < 0  <=>  VA < 128  <=>  bit 7 clear
+                    const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (va & 0x00000080u) == 0);
+                    const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (va & 0x00800000u) == 0);
+                    if (lane == 0) {
+                        const int e = c * M + (wd / S) * Q + (wd % S);
+                        hb[e >> 5] = b0;
+                        hb[(e + S) >> 5] = b1;
+                    }
+                    const uint32_t van = 0x00ff00ffu - va;
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).col == c) {
+                            constexpr int k = pos_in_col<P>(b);
+                            // C = 127 - clamp(va - u, -127, 127)
+                            const uint32_t cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
+                            if constexpr (P::blk(b).isp) {
+                                constexpr int ps = count_p<P>(b);
+                                msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
+                            } else {
+                                idm[count_i<P>(b)][wi] = cv;
+                            }
+                        }
+                    });
+                });
+            }
+            __syncthreads();
+
+            // ================= check phase (:391-405 and :422-447) =================
+#pragma unroll
+            for (int wi = 0; wi < WPT; wi++) {
+                const int wd = tid + wi * NT;
+                static_for<0, NROW>([&](auto ri) {
+                    constexpr int r = decltype(ri)::value;
+                    constexpr int DC = row_degree<P>(r);
+                    uint32_t a[kMaxDeg], ck[kMaxDeg], mu[kMaxDeg];
+                    uint32_t sx = 0;
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).row == r) {
+                            constexpr int k = pos_in_row<P>(b);
+                            uint32_t cv;
+                            if constexpr (P::blk(b).isp) cv = msg[count_p<P>(b) * (M / 2) + wd];
+                            else cv = idm[count_i<P>(b)][wi];
+                            const uint32_t old = cc[b][wi];
+                            const uint32_t x = (cv ^ old) & (cv ^ (old + 0x00010001u));   // bit 7: sign flipped and old != 0
+                            const uint32_t km = prmt_sign7(x);
+                            const uint32_t cor = (cv & ~km) | (0x007f007fu & km);         // killed -> v = 0
+                            cc[b][wi] = cor;
+                            ck[k] = cor;
+                            a[k] = __vmaxu2(cor, 0x00fe00feu - cor);                       // |v| + 127
+                            sx ^= cor;                                                     // bit 7: product of signs
+                        }
+                    });
+                    min_excluding_self<DC>(a, mu);
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).row == r) {
+                            constexpr int k = pos_in_row<P>(b);
+                            const uint32_t nm = prmt_sign7(sx ^ ck[k]);                    // lanes whose u is negative
+                            const uint32_t kk = __vadd2(nm, 0xff81ff81u);                  // -127 or -128
+                            const uint32_t u = __vadd2(mu[k], kk) ^ nm;                    // +-(mu - 127)
+                            if constexpr (P::blk(b).isp) msg[count_p<P>(b) * (M / 2) + wd] = u;
+                            else idm[count_i<P>(b)][wi] = u;
+                        }
+                    });
+                });
+            }
+            // ---- parity of the marginals' hard bits, one thread per 32 checks (:445-453) ----
+            uint32_t synd = 0;
+            if (tid < SYW) {
+                const int i0 = (tid * 32) % M, r = (tid * 32) / M;
+                const int q = i0 / Q, iq0 = i0 % Q;
+                static_for<0, NB>([&](auto bi) {
+                    constexpr int b = decltype(bi)::value;
+                    if (P::blk(b).row == r) {
+                        constexpr int col = P::blk(b).col;
+                        if constexpr (P::blk(b).isp) {
+                            const int qv = ((int)prm.theta[b] + q) & 3;
+                            const int s = ((int)prm.phi[b][q] + iq0) & (Q - 1);
+                            const int base = (col * M + qv * Q) >> 5;
+                            const int w0 = s >> 5, w1 = (w0 + 1) & (Q / 32 - 1);
+                            synd ^= __funnelshift_r(hb[base + w0], hb[base + w1], s & 31);
+                        } else {
+                            synd ^= hb[(col * M + i0) >> 5];
+                        }
+                    }
+                });
+            }
+            if (__syncthreads_or(synd != 0) == 0) {
+                ok = true;
+                iters_run = iter;                                                          // :462
+                break;
+            }
+        }
+
+        // ---- output: hard decisions of all n+p marginals, MSB first (:455-461, :466-473) ----
+        uint8_t *out = out_all + frame * (unsigned long long)(NV / 8);
+        const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+        for (int i = tid; i < HBW; i += NT) {
+            const uint32_t rev = __brev(hb[i]);                    // variable 32i at bit 31
+            if (aligned) {
+                reinterpret_cast<uint32_t *>(out)[i] = __byte_perm(rev, 0, 0x0123);
+            } else {
+                out[4 * i + 0] = (uint8_t)(rev >> 24); out[4 * i + 1] = (uint8_t)(rev >> 16);
+                out[4 * i + 2] = (uint8_t)(rev >> 8);  out[4 * i + 3] = (uint8_t)rev;
+            }
+        }
+        if (tid == 0) {
+            if (success) success[frame] = ok ? 1 : 0;
+            if (iters_out) iters_out[frame] = iters_run;
+        }
+        __syncthreads();   // hb / msg / s_frame are reused by the next frame
+    }
+}
+
+template <int RATE> bool structure_matches(const CodeInfo &c) {
+    typedef Proto<RATE> P;
+    if (c.n_blocks != P::NB || c.cols != P::NCOL || c.rows != P::NROW) return false;
+    for (int b = 0; b < P::NB; b++) {
+        const Block &blk = c.blocks[b];
+        const Blk want = P::blk(b);
+        if (blk.row != want.row || blk.col != want.col) return false;
+        if ((blk.kind == kPermutation) != (want.isp != 0)) return false;
+        if (blk.kind == kIdentity && blk.shift != 0) return false;
+        if (blk.edge_offset != b * c.m) return false;
+    }
+    return true;
+}
+
+struct Counters {
+    unsigned long long *ring = nullptr;
+    int next = 0;
+    int device = -1;
+};
+constexpr int kCounterRing = 1024;
+Counters g_counters[16];
+
+cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **out) {
+    Counters *cs = &g_counters[device & 15];   // launchers run under the per-device context mutex
+    if (cs->device < 0) {
+        cudaError_t e = cudaMalloc(&cs->ring, kCounterRing * sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+        cs->device = device;
+    }
+    *out = cs->ring + cs->next;
+    cs->next = (cs->next + 1) % kCounterRing;
+    return cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream);
+}
+
+template <int RATE, int M, int WPT>
+cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uint8_t *output, size_t batch,
+                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    typedef Proto<RATE> P;
+    constexpr int NP = count_p<P>(P::NB);
+    constexpr int NT = M / 2 / WPT;
+    TmParams prm{};
+    for (int b = 0; b < P::NB; b++) {
+        prm.theta[b] = (uint8_t)c.blocks[b].theta;
+        for (int j = 0; j < 4; j++) prm.phi[b][j] = (uint16_t)c.blocks[b].phi[j];
+    }
+    const size_t smem = ((size_t)NP * (M / 2) + (size_t)P::NCOL * M / 32) * sizeof(uint32_t);
+    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT>;
+    static bool configured[16] = {};
+    if (!configured[ctx.device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[ctx.device & 15] = true;
+    }
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
+    if (grid > batch) grid = batch;
+    unsigned long long *counter = nullptr;
+    e = next_counter(ctx.device, stream, &counter);
+    if (e != cudaSuccess) return e;
+    const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
+    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, llrs, output, (unsigned long long)batch, mi, success, iters, counter);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Returns true (and launches) if a specialised kernel exists for (code, i8).
+bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
+                            size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                            cudaError_t *err) {
+    const CodeInfo &c = *code_info(code);
+    const int8_t *l = static_cast<const int8_t *>(llrs);
+    switch (code) {
+        case 4:
+            if (!structure_matches<1>(c) || c.m != 256) return false;
+            *err = launch_tm<1, 256, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            return true;
+        case 5:
+            if (!structure_matches<0>(c) || c.m != 512) return false;
+            *err = launch_tm<0, 512, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            return true;
+        case 6:
+            if (!structure_matches<2>(c) || c.m != 512) return false;
+            *err = launch_tm<2, 512, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            return true;
+        case 7:
+            if (!structure_matches<1>(c) || c.m != 1024) return false;
+            *err = launch_tm<1, 1024, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            return true;
+        case 8:
+            if (!structure_matches<0>(c) || c.m != 2048) return false;
+            *err = launch_tm<0, 2048, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            return true;
+        default:
+            return false;
+    }
+}
+
+bool has_decode_ms_tm_i8(int code) { return code >= 4 && code <= 8; }
+
+}  // namespace ldpc

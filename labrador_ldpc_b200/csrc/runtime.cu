@@ -21,7 +21,18 @@ cudaError_t launch_decode_ms_generic(DeviceCtx &ctx, int code, int llr_type, con
                                      size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
                                      cudaStream_t stream);
 
+bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
+                            size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                            cudaError_t *err);
+bool has_decode_ms_tm_i8(int code);
+
 namespace {
+
+// LABRADOR_LDPC_FORCE_GENERIC=1 routes everything through the generic kernel (A/B testing only).
+bool force_generic() {
+    static const bool v = [] { const char *e = getenv("LABRADOR_LDPC_FORCE_GENERIC"); return e && e[0] == '1'; }();
+    return v;
+}
 
 std::atomic<unsigned long long> g_launches{0};
 thread_local std::string t_last_error;
@@ -225,11 +236,15 @@ cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void 
                              size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
                              cudaStream_t stream) {
     if (batch == 0) return cudaSuccess;
+    if (llr_type == kI8 && !force_generic()) {
+        cudaError_t err = cudaSuccess;
+        if (launch_decode_ms_tm_i8(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err)) return err;
+    }
     return launch_decode_ms_generic(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream);
 }
 
 const char *decode_ms_kernel_name(int code, int llr_type) {
-    (void)code;
+    if (llr_type == kI8 && has_decode_ms_tm_i8(code) && !force_generic()) return "ms_tm_s16x2<i8>";
     static const char *names[kNumLlrTypes] = {"ms_generic<i8>", "ms_generic<i16>", "ms_generic<i32>",
                                               "ms_generic<f32>", "ms_generic<f64>"};
     if (llr_type < 0 || llr_type >= kNumLlrTypes) return "invalid";
