@@ -154,7 +154,8 @@ template <int RATE, int M, int WPT>
 __global__ void __launch_bounds__(M / 2 / WPT)
 decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
                        unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
-                       uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+                       uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
+                       const uint32_t one /* == 1: keeps the borrow-free subtractions on the FMA pipe (IMAD) */) {
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
     constexpr int NP = count_p<P>(NB), NI = NB - NP;
@@ -164,6 +165,15 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
     constexpr int SYW = NC / 32;           // syndrome words
     static_assert(S >= 32 && S % 32 == 0, "lane pairing needs at least one warp per half quarter");
     static_assert(SYW <= NT, "one thread per syndrome word");
+    // Two-stage exit test.  Row 0 of every TM prototype is {I at column CA, I and P at the punctured column CP}.
+    // Stage 1 (every iteration) packs the hard bits of those two columns only and tests the M row-0 checks; a
+    // non-zero row-0 syndrome proves the codeword is not yet valid.  Only when row 0 is clean are the remaining
+    // columns' hard bits (kept as one packed register per thread) ballot-packed and rows 1..2 tested.
+    constexpr int CA = P::blk(0).col, CP = NCOL - 1;
+    static_assert(P::blk(0).row == 0 && !P::blk(0).isp && P::blk(1).row == 0 && P::blk(1).col == CP && !P::blk(1).isp &&
+                  P::blk(2).row == 0 && P::blk(2).col == CP && P::blk(2).isp && P::blk(3).row == 1,
+                  "row 0 must be I(CA) + I(CP) + P(CP)");
+    static_assert(NCOL - 2 <= 9, "packed hard bits use bits 7..15 / 23..31");
 
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t *msg = smem_u32;                       // [NP][M/2] permutation-block messages, check order
@@ -193,6 +203,14 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
             }
         });
     }
+
+    uint32_t hbw[WPT];    // word index (within a column) of this warp's 32 hard bits, lane 0 / lane 1 = +S/32
+#pragma unroll
+    for (int wi = 0; wi < WPT; wi++) {
+        const int wd = tid + wi * NT;
+        hbw[wi] = (uint32_t)(((wd / S) * Q + (wd % S)) >> 5);
+    }
+    const uint32_t c254 = 0x00fe00feu * one, c255 = 0x00ff00ffu * one;
 
     for (;;) {
         if (tid == 0) s_frame = atomicAdd(counter, 1ull);
@@ -230,11 +248,32 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
 
         unsigned iters_run = max_iters;
         bool ok = false;
+        uint32_t pack[WPT];           // hard bits of the columns not covered by stage 1
+        bool hb_complete = true;      // hb[] holds every column's hard bits of the latest variable phase
+        // ballot-packs the deferred columns' hard bits into hb[] (stage 2 / final output)
+        auto flush_pack = [&]() {
+#pragma unroll
+            for (int wi = 0; wi < WPT; wi++) {
+                int kpos = 0;
+                static_for<0, NCOL>([&](auto ci) {
+                    constexpr int c = NCOL - 1 - decltype(ci)::value;     // last packed column sits at bit 7 / 23
+                    if constexpr (c != CA && c != CP) {
+                        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (pack[wi] >> (7 + kpos)) & 1u);
+                        const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (pack[wi] >> (23 + kpos)) & 1u);
+                        if (lane == 0) {
+                            hb[hbw[wi] + c * M / 32] = b0;
+                            hb[hbw[wi] + (c * M + S) / 32] = b1;
+                        }
+                        kpos++;
+                    }
+                });
+            }
+        };
         for (unsigned iter = 0; iter < max_iters; iter++) {
             // ================= variable phase (:382-411 and :421) =================
 #pragma unroll
             for (int wi = 0; wi < WPT; wi++) {
-                const int wd = tid + wi * NT;
+                pack[wi] = 0;
                 static_for<0, NCOL>([&](auto ci) {
                     constexpr int c = decltype(ci)::value;
                     uint32_t va = Lb[c][wi];
@@ -255,14 +294,17 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                         }
                     });
                     // hard decisions of the marginals: va < 0  <=>  VA < 128  <=>  bit 7 clear
-                    const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (va & 0x00000080u) == 0);
-                    const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (va & 0x00800000u) == 0);
-                    if (lane == 0) {
-                        const int e = c * M + (wd / S) * Q + (wd % S);
-                        hb[e >> 5] = b0;
-                        hb[(e + S) >> 5] = b1;
+                    if constexpr (c == CA || c == CP) {
+                        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (va & 0x00000080u) == 0);
+                        const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (va & 0x00800000u) == 0);
+                        if (lane == 0) {
+                            hb[hbw[wi] + c * M / 32] = b0;
+                            hb[hbw[wi] + (c * M + S) / 32] = b1;
+                        }
+                    } else {
+                        pack[wi] = pack[wi] * (one + one) + (~va & 0x00800080u);   // older columns move up one bit
                     }
-                    const uint32_t van = 0x00ff00ffu - va;
+                    const uint32_t van = c255 * one - va;
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).col == c) {
@@ -303,7 +345,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                             const uint32_t cor = (cv & ~km) | (0x007f007fu & km);         // killed -> v = 0
                             cc[b][wi] = cor;
                             ck[k] = cor;
-                            a[k] = __vmaxu2(cor, 0x00fe00feu - cor);                       // |v| + 127
+                            a[k] = __vmaxu2(cor, c254 * one - cor);                       // |v| + 127
                             sx ^= cor;                                                     // bit 7: product of signs
                         }
                     });
@@ -321,10 +363,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                     });
                 });
             }
-            // ---- parity of the marginals' hard bits, one thread per 32 checks (:445-453) ----
-            uint32_t synd = 0;
-            if (tid < SYW) {
-                const int i0 = (tid * 32) % M, r = (tid * 32) / M;
+            // ---- parity of the marginals' hard bits (:445-453), one thread per 32 checks ----
+            auto syndrome_word = [&](int sw) {
+                uint32_t synd = 0;
+                const int i0 = (sw * 32) % M, r = (sw * 32) / M;
                 const int q = i0 / Q, iq0 = i0 % Q;
                 static_for<0, NB>([&](auto bi) {
                     constexpr int b = decltype(bi)::value;
@@ -341,12 +383,29 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                         }
                     }
                 });
-            }
+                return synd;
+            };
+            // stage 1: row 0 only (its hard bits were packed in this iteration's variable phase)
+            uint32_t synd = 0;
+            if (tid < M / 32) synd = syndrome_word(tid);
+            hb_complete = false;
             if (__syncthreads_or(synd != 0) == 0) {
-                ok = true;
-                iters_run = iter;                                                          // :462
-                break;
+                // stage 2: row 0 is clean -- pack the other columns and test rows 1..NROW-1
+                flush_pack();
+                hb_complete = true;
+                __syncthreads();
+                synd = 0;
+                for (int sw = M / 32 + tid; sw < SYW; sw += NT) synd |= syndrome_word(sw);
+                if (__syncthreads_or(synd != 0) == 0) {
+                    ok = true;
+                    iters_run = iter;                                                      // :462
+                    break;
+                }
             }
+        }
+        if (!hb_complete) {       // decoding failed: the output is the hard decision of the last marginals (:466-473)
+            flush_pack();
+            __syncthreads();
         }
 
         // ---- output: hard decisions of all n+p marginals, MSB first (:455-461, :466-473) ----
@@ -432,7 +491,7 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
     e = next_counter(ctx.device, stream, &counter);
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, llrs, output, (unsigned long long)batch, mi, success, iters, counter);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, llrs, output, (unsigned long long)batch, mi, success, iters, counter, 1u);
     count_launch();
     return cudaGetLastError();
 }
