@@ -40,6 +40,7 @@
 // the marginals' hard bits, the syndrome is XORs of funnel-shifted words.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "runtime.h"
@@ -523,7 +524,10 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            *err = launch_tm<0, 2048, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (getenv("LABRADOR_LDPC_TM_WPT") && getenv("LABRADOR_LDPC_TM_WPT")[0] == '2')
+                *err = launch_tm<0, 2048, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else
+                *err = launch_tm<0, 2048, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;

@@ -166,3 +166,18 @@ def test_product_never_touches_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in text and "liboracle" not in text and "oracle/" not in text.replace(
                     "oracle/ccsds_tables.h", ""), (dirpath, f)
+
+
+def test_rust_binding_matches_header(ldpc):
+    """rust/labrador-ldpc-b200 cannot be compiled here (no Rust toolchain); at least every
+    extern it declares must exist in the header and be exported by the shared library."""
+    src = open(os.path.join(ROOT, "rust", "labrador-ldpc-b200", "src", "lib.rs")).read()
+    externs = set(re.findall(r"pub fn (labrador_ldpc_[a-z0-9_]+)\s*\(", src))
+    assert len(externs) >= 25
+    declared = set(header_symbols())
+    for name in externs:
+        assert name in declared, name
+        assert hasattr(ldpc.lib, name), name
+    # enum discriminants are the reference's (src/codes/mod.rs:37-66)
+    for i, name in enumerate(NAMES):
+        assert re.search(r"\b%s = %d\b" % (name, i), src), name
