@@ -33,6 +33,7 @@ EBN0_DB = 2.0
 MAX_ITERS = 100
 N, K_INFO, OUT_LEN, EDGES = 8192, 4096, 1280, 30720
 ALG_BYTES_PER_FRAME = N * 1 + OUT_LEN + 8          # LLRs in + packed output + flags
+NCU_DRAM_BYTES_PER_FRAME = 9399                    # profiles/r01_tm8192_ncu.md (615.98 MB / 65536 frames)
 WORKLOAD = "TM8192 (k=4096, r=1/2) decode_ms i8 LLRs, Eb/N0 2 dB, max_iters 100"
 
 
@@ -307,7 +308,9 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": NCU_DRAM_BYTES_PER_FRAME * frames, "peak_source": peak_src,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                       "(65536 frames, profiles/r01_tm8192_ncu.md) scaled to this launch's frame count",
                      "algorithmic_bytes_per_frame": ALG_BYTES_PER_FRAME,
                      "note": "decode_ms is bound by the integer ALU pipe and shared memory, not HBM (DESIGN.md); "
                              "see roofline_alu"},

@@ -24,6 +24,12 @@ from . import _build
 __all__ = ["LDPCCode", "LdpcError", "lib", "LLR_TYPES", "init", "shutdown", "kernel_launch_count"]
 
 _LIB_PATH = _build.LIB
+if os.path.exists(_LIB_PATH) and _build.needs_build() and os.environ.get("LABRADOR_LDPC_NO_REBUILD") != "1":
+    # the shared object is older than the sources: rebuild rather than run a stale binary
+    try:
+        _build.build()
+    except Exception as exc:   # pragma: no cover
+        raise ImportError("labrador_ldpc_b200: liblabrador_ldpc.so is stale and rebuilding failed: %s" % exc)
 if not os.path.exists(_LIB_PATH):
     raise ImportError(
         "labrador_ldpc_b200: %s is missing -- build it with `python -m labrador_ldpc_b200._build` "
