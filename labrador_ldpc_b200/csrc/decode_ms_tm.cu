@@ -38,6 +38,7 @@
 //       = parity of the other edges' signs (:398-405), as two's complement.
 // The per-iteration parity test (:445-453) runs bit-packed: warp ballots pack
 // the marginals' hard bits, the syndrome is XORs of funnel-shifted words.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -135,23 +136,49 @@ __device__ __forceinline__ uint32_t lane_rot(uint32_t x, uint32_t sh) { return _
 
 constexpr int kMaxDeg = 18;
 
+// ---- FMA-pipe arithmetic on small integers held as fp16 bit patterns ----
+// A 16-bit lane holding the integer k (0 <= k < 1024) IS the fp16 subnormal k * 2^-24, and a set bit 15
+// makes it -k.  fp16 add / fma on such values is exact integer arithmetic (|result| < 2048), runs on the
+// FMA pipe (HFMA2 / HADD2) and leaves the saturated ALU pipe alone (profiles/r01_pipe_ubench.md).
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ uint32_t f_relu_add(uint32_t a, uint32_t b) {          // max(a + b, 0)
+    return h2u(__hfma2_relu(u2h(a), u2h(0x3C003C00u), u2h(b)));
+}
+__device__ __forceinline__ uint32_t f_relu_sub(uint32_t a, uint32_t b) {          // max(a - b, 0)
+    return h2u(__hfma2_relu(u2h(b), u2h(0xBC00BC00u), u2h(a)));
+}
+__device__ __forceinline__ uint32_t f_sub(uint32_t a, uint32_t b) { return h2u(__hsub2(u2h(a), u2h(b))); }
+// min of two non-negative lanes: on the FMA pipe (2 ops: a - relu(a - b)) or the ALU pipe (1 VIMNMX)
+template <bool ON_FMA> __device__ __forceinline__ uint32_t pmin(uint32_t a, uint32_t b) {
+    if constexpr (ON_FMA) return f_sub(a, f_relu_sub(a, b));
+    else return __vminu2(a, b);
+}
+
 // Minimum over "all the other edges" for every edge of one check word: prefix/suffix minima.
-template <int DC> __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
+// SUF_F / PRE_F / COMB_F choose the pipe of the three groups of DC-2 minima (pipe balancing).
+template <int DC, bool SUF_F, bool PRE_F, bool COMB_F>
+__device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
     uint32_t suf[kMaxDeg];
     suf[DC - 1] = a[DC - 1];
 #pragma unroll
-    for (int k = DC - 2; k >= 1; k--) suf[k] = __vminu2(a[k], suf[k + 1]);
+    for (int k = DC - 2; k >= 1; k--) suf[k] = pmin<SUF_F>(a[k], suf[k + 1]);
     uint32_t pre = a[0];
     mu[0] = suf[1];
 #pragma unroll
     for (int k = 1; k < DC - 1; k++) {
-        mu[k] = __vminu2(pre, suf[k + 1]);
-        pre = __vminu2(pre, a[k]);
+        mu[k] = pmin<COMB_F>(pre, suf[k + 1]);
+        pre = pmin<PRE_F>(pre, a[k]);
     }
     mu[DC - 1] = pre;
 }
 
-template <int RATE, int M, int WPT>
+// Arithmetic variants of the kernel (kept side by side for A/B measurement):
+//   ARITH 1: integer lanes throughout (VIADDMNMX chain, two's-complement u)      -- ALU-pipe bound
+//   ARITH 3: ARITH 1 with |v| by VABSDIFF4 (no +127 offset to carry around)
+//   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
+//            part of the minima on the FMA pipe (bits of KNOBS: 1 cv-min, 2 suffix, 4 prefix, 8 combine)
+template <int RATE, int M, int WPT, int ARITH, int KNOBS>
 __global__ void __launch_bounds__(M / 2 / WPT)
 decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
                        unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
@@ -211,7 +238,8 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
         const int wd = tid + wi * NT;
         hbw[wi] = (uint32_t)(((wd / S) * Q + (wd % S)) >> 5);
     }
-    const uint32_t c254 = 0x00fe00feu * one, c255 = 0x00ff00ffu * one;
+    const uint32_t c254 = 0x00fe00feu * one, c255 = 0x00ff00ffu * one, c256 = one << 8;
+    constexpr bool CV_F = (KNOBS & 1) != 0, SUF_F = (KNOBS & 2) != 0, PRE_F = (KNOBS & 4) != 0, COMB_F = (KNOBS & 8) != 0;
 
     for (;;) {
         if (tid == 0) s_frame = atomicAdd(counter, 1ull);
@@ -291,9 +319,24 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                                 u = idm[count_i<P>(b)][wi];
                             }
                             ub[k] = u;
-                            va = __viaddmin_s16x2_relu(va, u, 0x00ff00ffu);      // saturating_add, ascending idx
+                            if constexpr (ARITH != 2) {
+                                va = __viaddmin_s16x2_relu(va, u, 0x00ff00ffu);  // saturating_add, ascending idx
+                            } else if constexpr ((k & 1) == 0) {                 // state is VA -> 255 - clamp(VA + u)
+                                va = f_relu_sub(0x00ff00ffu, f_relu_add(va, u));
+                            } else {                                             // state is 255 - VA -> clamp(VA + u)
+                                va = f_relu_sub(0x00ff00ffu, f_relu_sub(va, u));
+                            }
                         }
                     });
+                    uint32_t van;
+                    if constexpr (ARITH != 2) {
+                        van = c255 * one - va;
+                    } else if constexpr ((col_degree<P>(c) & 1) == 0) {          // chain ended in the VA form
+                        van = f_sub(0x00ff00ffu, va);
+                    } else {                                                     // chain ended in the 255 - VA form
+                        van = va;
+                        va = f_sub(0x00ff00ffu, van);
+                    }
                     // hard decisions of the marginals: va < 0  <=>  VA < 128  <=>  bit 7 clear
                     if constexpr (c == CA || c == CP) {
                         const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (va & 0x00000080u) == 0);
@@ -305,13 +348,14 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                     } else {
                         pack[wi] = pack[wi] * (one + one) + (~va & 0x00800080u);   // older columns move up one bit
                     }
-                    const uint32_t van = c255 * one - va;
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).col == c) {
                             constexpr int k = pos_in_col<P>(b);
                             // C = 127 - clamp(va - u, -127, 127)
-                            const uint32_t cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
+                            uint32_t cv;
+                            if constexpr (ARITH != 2) cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
+                            else cv = pmin<CV_F>(f_relu_add(van, ub[k]), 0x00fe00feu);
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
                                 msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
@@ -346,18 +390,29 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                             const uint32_t cor = (cv & ~km) | (0x007f007fu & km);         // killed -> v = 0
                             cc[b][wi] = cor;
                             ck[k] = cor;
-                            a[k] = __vmaxu2(cor, c254 * one - cor);                       // |v| + 127
+                            if constexpr (ARITH == 1) a[k] = __vmaxu2(cor, c254 * one - cor);    // |v| + 127
+                            else a[k] = __vabsdiffu4(cor, 0x007f007fu);                          // |v|
                             sx ^= cor;                                                     // bit 7: product of signs
                         }
                     });
-                    min_excluding_self<DC>(a, mu);
+                    if constexpr (ARITH == 1) min_excluding_self<DC, false, false, false>(a, mu);
+                    else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).row == r) {
                             constexpr int k = pos_in_row<P>(b);
-                            const uint32_t nm = prmt_sign7(sx ^ ck[k]);                    // lanes whose u is negative
-                            const uint32_t kk = __vadd2(nm, 0xff81ff81u);                  // -127 or -128
-                            const uint32_t u = __vadd2(mu[k], kk) ^ nm;                    // +-(mu - 127)
+                            uint32_t u;
+                            if constexpr (ARITH == 1) {
+                                const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
+                                const uint32_t kk = __vadd2(nm, 0xff81ff81u);              // -127 or -128
+                                u = __vadd2(mu[k], kk) ^ nm;                               // +-(mu - 127), two's complement
+                            } else if constexpr (ARITH == 3) {
+                                const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
+                                u = __vadd2(mu[k], nm) ^ nm;                               // +-mu, two's complement
+                            } else {
+                                const uint32_t zs = (sx ^ ck[k]) & 0x00800080u;            // sign of u at bit 7
+                                u = zs * c256 + mu[k];                                     // sign-magnitude: bit 15 | mu
+                            }
                             if constexpr (P::blk(b).isp) msg[count_p<P>(b) * (M / 2) + wd] = u;
                             else idm[count_i<P>(b)][wi] = u;
                         }
@@ -463,7 +518,7 @@ cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **o
     return cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream);
 }
 
-template <int RATE, int M, int WPT>
+template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1>
 cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     typedef Proto<RATE> P;
@@ -475,7 +530,7 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
         for (int j = 0; j < 4; j++) prm.phi[b][j] = (uint16_t)c.blocks[b].phi[j];
     }
     const size_t smem = ((size_t)NP * (M / 2) + (size_t)P::NCOL * M / 32) * sizeof(uint32_t);
-    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT>;
+    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -499,6 +554,18 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
 
 }  // namespace
 
+// Variant selection.  Three arithmetic variants are compiled per code; the default per code is the one that
+// measured fastest on B200 (profiles/r01_tm_variants.md).  LABRADOR_LDPC_TM_ARITH=1|2|3 overrides (A/B runs).
+template <int RATE, int M>
+cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const int8_t *l, uint8_t *output,
+                              size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 0; }();
+    const int arith = forced ? forced : default_arith;
+    if (arith == 1) return launch_tm<RATE, M, 1, 1, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 3) return launch_tm<RATE, M, 1, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    return launch_tm<RATE, M, 1, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+}
+
 // Returns true (and launches) if a specialised kernel exists for (code, i8).
 bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
@@ -508,26 +575,23 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
     switch (code) {
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            *err = launch_tm<1, 256, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<1, 256>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
-            *err = launch_tm<0, 512, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<0, 512>(2, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            *err = launch_tm<2, 512, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<2, 512>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            *err = launch_tm<1, 1024, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<1, 1024>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            if (getenv("LABRADOR_LDPC_TM_WPT") && getenv("LABRADOR_LDPC_TM_WPT")[0] == '2')
-                *err = launch_tm<0, 2048, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else
-                *err = launch_tm<0, 2048, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<0, 2048>(2, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;
