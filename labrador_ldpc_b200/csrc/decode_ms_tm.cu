@@ -134,6 +134,30 @@ __device__ __forceinline__ uint32_t prmt_sign7(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t lane_rot(uint32_t x, uint32_t sh) { return __funnelshift_l(x, x, sh); }
 
+// ---- bulk asynchronous copy (TMA, cp.async.bulk) of one frame's LLRs into shared memory ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// one thread: arm the barrier with the byte count and start the copy (dst, src and bytes are multiples of 16)
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order earlier generic-proxy reads of dst
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
 constexpr int kMaxDeg = 18;
 
 // ---- FMA-pipe arithmetic on small integers held as fp16 bit patterns ----
@@ -206,7 +230,9 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t *msg = smem_u32;                       // [NP][M/2] permutation-block messages, check order
     uint32_t *hb = msg + NP * (M / 2);              // [HBW] packed hard decisions, bit i of word j = variable 32j+i
-    __shared__ unsigned long long s_frame;
+    int8_t *stage = reinterpret_cast<int8_t *>(hb + ((HBW + 3) & ~3));   // [2][N] LLR staging (bulk-copy destination)
+    __shared__ unsigned long long s_frame[2];
+    __shared__ __align__(8) uint64_t s_bar[2];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -241,12 +267,37 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
     const uint32_t c254 = 0x00fe00feu * one, c255 = 0x00ff00ffu * one, c256 = one << 8;
     constexpr bool CV_F = (KNOBS & 1) != 0, SUF_F = (KNOBS & 2) != 0, PRE_F = (KNOBS & 4) != 0, COMB_F = (KNOBS & 8) != 0;
 
+    // Frames are claimed one ahead: while frame f is decoded, the LLRs of the next claimed frame are
+    // already in flight (one 16-byte-aligned bulk copy of N bytes, completion on an mbarrier).
+    const bool use_bulk = (reinterpret_cast<uintptr_t>(llrs_all) & 15u) == 0;   // unaligned caller buffer: plain loads
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned long long f0 = atomicAdd(counter, 1ull);
+        s_frame[0] = f0;
+        if (use_bulk && f0 < batch) bulk_load(stage, llrs_all + f0 * (unsigned long long)N, N, &s_bar[0]);
+    }
+    __syncthreads();
+    unsigned cur = 0, bar_parity = 0;    // bit b of bar_parity = phase parity of s_bar[b]
+
     for (;;) {
-        if (tid == 0) s_frame = atomicAdd(counter, 1ull);
-        __syncthreads();
-        const unsigned long long frame = s_frame;
+        const unsigned long long frame = s_frame[cur];
         if (frame >= batch) break;
-        const int8_t *llr = llrs_all + frame * (unsigned long long)N;
+        if (tid == 0) {                  // claim the next frame and start its copy into the other buffer
+            const unsigned long long fn = atomicAdd(counter, 1ull);
+            s_frame[cur ^ 1] = fn;
+            if (use_bulk && fn < batch)
+                bulk_load(stage + (cur ^ 1) * N, llrs_all + fn * (unsigned long long)N, N, &s_bar[cur ^ 1]);
+        }
+        const int8_t *llr;
+        if (use_bulk) {
+            mbar_wait(&s_bar[cur], (bar_parity >> cur) & 1u);
+            bar_parity ^= 1u << cur;
+            llr = stage + cur * N;
+        } else {
+            llr = llrs_all + frame * (unsigned long long)N;
+        }
 
         // ---- per-frame state: everything zero, every call (:368, :374) ----
         uint32_t Lb[NCOL][WPT];       // channel LLR + 128 (punctured column: 128)
@@ -443,7 +494,9 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
             };
             // stage 1: row 0 only (its hard bits were packed in this iteration's variable phase)
             uint32_t synd = 0;
-            if (tid < M / 32) synd = syndrome_word(tid);
+            // (done by the HIGHEST-numbered warps: the SM's arbiter favours high warp ids, so the warps with the
+            //  extra work are the ones that reach the barrier early anyway)
+            if (tid >= NT - M / 32) synd = syndrome_word(tid - (NT - M / 32));
             hb_complete = false;
             if (__syncthreads_or(synd != 0) == 0) {
                 // stage 2: row 0 is clean -- pack the other columns and test rows 1..NROW-1
@@ -480,7 +533,8 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
             if (success) success[frame] = ok ? 1 : 0;
             if (iters_out) iters_out[frame] = iters_run;
         }
-        __syncthreads();   // hb / msg / s_frame are reused by the next frame
+        __syncthreads();   // hb / msg / stage / s_frame are reused by the next frame
+        cur ^= 1;
     }
 }
 
@@ -529,7 +583,8 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
         prm.theta[b] = (uint8_t)c.blocks[b].theta;
         for (int j = 0; j < 4; j++) prm.phi[b][j] = (uint16_t)c.blocks[b].phi[j];
     }
-    const size_t smem = ((size_t)NP * (M / 2) + (size_t)P::NCOL * M / 32) * sizeof(uint32_t);
+    const size_t smem = ((size_t)NP * (M / 2) + (((size_t)P::NCOL * M / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) +
+                        2 * (size_t)(P::NCOL - 1) * M;   // messages + hard bits + two LLR staging buffers
     auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
@@ -561,6 +616,13 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 0; }();
     const int arith = forced ? forced : default_arith;
+    if constexpr (M == 2048) {   // TM8192: 2 words per thread (512 threads x <=128 registers) is also compiled
+        static const int wpt = [] { const char *e = getenv("LABRADOR_LDPC_TM_WPT"); return e ? atoi(e) : 2; }();
+        if (wpt == 2) {
+            if (arith == 3) return launch_tm<RATE, M, 2, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            return launch_tm<RATE, M, 2, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+        }
+    }
     if (arith == 1) return launch_tm<RATE, M, 1, 1, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 3) return launch_tm<RATE, M, 1, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     return launch_tm<RATE, M, 1, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -591,7 +653,7 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            *err = launch_tm_variant<0, 2048>(2, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<0, 2048>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;

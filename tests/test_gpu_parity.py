@@ -386,3 +386,21 @@ def test_launch_counter_and_kernel_names(ldpc):
     assert ldpc.kernel_launch_count() > before
     for ty in ("i8", "i16", "i32", "f32", "f64"):
         assert c.decode_ms_kernel_name(ty).startswith("ms_")
+
+
+def test_unaligned_device_llrs_take_plain_load_path(ldpc, oracle):
+    """The TM kernel stages frames with 16-byte bulk copies; a misaligned device buffer must fall back to
+    plain loads and still match the oracle (and odd batch sizes exercise the claim-ahead frame queue)."""
+    import torch
+    code = 8
+    c = ldpc.LDPCCode(code)
+    for batch, off in ((1, 0), (3, 5), (149, 0), (301, 1)):
+        _, _, llrs = make_frames(oracle, code, batch, 2.0, seed=900 + batch, ty="i8")
+        want = oracle.decode_ms_batch(code, llrs, 60, nthreads=8)
+        raw = torch.zeros(llrs.size + 16, dtype=torch.int8, device="cuda")
+        view = raw[off:off + llrs.size].view(batch, c.n())
+        view.copy_(torch.from_numpy(llrs))
+        assert view.data_ptr() % 16 == off % 16
+        got = c.decode_ms_batch(view, 60)
+        torch.cuda.synchronize()
+        assert_exact([g.cpu().numpy() for g in got], want, "batch=%d offset=%d" % (batch, off))
