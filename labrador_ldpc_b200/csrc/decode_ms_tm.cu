@@ -200,6 +200,8 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 // Arithmetic variants of the kernel (kept side by side for A/B measurement):
 //   ARITH 1: integer lanes throughout (VIADDMNMX chain, two's-complement u)      -- ALU-pipe bound
 //   ARITH 3: ARITH 1 with |v| by VABSDIFF4 (no +127 offset to carry around)
+//   ARITH 4: ARITH 3 with u sent in sign-magnitude (1 LOP3 + 1 IMAD on the check side) and converted to
+//            two's complement on the FMA pipe by the variable side (fp16 magic-constant add); KNOBS as ARITH 2
 //   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
 //            part of the minima on the FMA pipe (bits of KNOBS: 1 cv-min, 2 suffix, 4 prefix, 8 combine)
 template <int RATE, int M, int WPT, int ARITH, int KNOBS>
@@ -369,6 +371,11 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                             } else {
                                 u = idm[count_i<P>(b)][wi];
                             }
+                            if constexpr (ARITH == 4) {
+                                // sign-magnitude (fp16 subnormal +-mu) -> two's complement, on the FMA pipe only:
+                                // +-mu*2^-24 + 1.5*2^-14 has the bit pattern 0x0600 +- mu; then subtract 0x0600 per lane
+                                u = __vadd2(h2u(__hadd2(u2h(u), u2h(0x06000600u))), 0xFA00FA00u);
+                            }
                             ub[k] = u;
                             if constexpr (ARITH != 2) {
                                 va = __viaddmin_s16x2_relu(va, u, 0x00ff00ffu);  // saturating_add, ascending idx
@@ -446,7 +453,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                             sx ^= cor;                                                     // bit 7: product of signs
                         }
                     });
-                    if constexpr (ARITH == 1) min_excluding_self<DC, false, false, false>(a, mu);
+                    if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
                     else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
@@ -620,11 +627,16 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
         static const int wpt = [] { const char *e = getenv("LABRADOR_LDPC_TM_WPT"); return e ? atoi(e) : 2; }();
         if (wpt == 2) {
             if (arith == 3) return launch_tm<RATE, M, 2, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 4) return launch_tm<RATE, M, 2, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 46) return launch_tm<RATE, M, 2, 4, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 42) return launch_tm<RATE, M, 2, 4, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             return launch_tm<RATE, M, 2, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         }
     }
     if (arith == 1) return launch_tm<RATE, M, 1, 1, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 3) return launch_tm<RATE, M, 1, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 4) return launch_tm<RATE, M, 1, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 46) return launch_tm<RATE, M, 1, 4, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     return launch_tm<RATE, M, 1, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
 }
 
