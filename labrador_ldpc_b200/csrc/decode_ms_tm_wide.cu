@@ -1,0 +1,355 @@
+// Specialised min-sum decoder for the TM codes with one element per lane: i16 / i32 / f32 LLRs
+// (and every LLR type on TM1280, whose M = 128 is too small for the packed-lane i8 kernel).
+//
+// Replaces LDPCCode::decode_ms::<T> (reference src/decoder.rs:347-475).  Same skeleton as
+// decode_ms_tm.cu -- thread t owns element t of every prototype column and every prototype row,
+// identity-block messages stay in registers, pi_k-block messages go through shared memory in check
+// order, u is never stored, two-stage bit-packed exit test -- but the arithmetic is the plain scalar
+// DecodeFrom semantics of llr_arith.cuh (reference src/decoder.rs:42-86):
+//   variable side  va = llr (+) u_0 (+) u_1 ...  in ascending edge index (:408), then v_j = va (-) u_j (:421)
+//   check side     self-correction against the previous v kept in a register (:422-426), min over the
+//                  other edges by prefix/suffix minima (= min1/min2 selection, :391-395), sign parity of
+//                  the other edges (:398-405).
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+
+#include "llr_arith.cuh"
+#include "runtime.h"
+#include "tm_common.cuh"
+
+namespace ldpc {
+using namespace tm;
+
+namespace {
+
+constexpr int kMaxDegW = 18;
+
+template <int RATE, int M, class T, int NT>
+__global__ void __launch_bounds__(NT)
+decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
+                         unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
+                         uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+    typedef Proto<RATE> P;
+    typedef Arith<T> A;
+    constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
+    constexpr int NP = count_p<P>(NB), NI = NB - NP;
+    constexpr int Q = M / 4, EPT = M / NT;
+    constexpr int NV = NCOL * M, N = (NCOL - 1) * M, NC = NROW * M;
+    constexpr int HBW = NV / 32, SYW = NC / 32;
+    constexpr int CA = P::blk(0).col, CP = NCOL - 1;      // the two columns row 0 touches (see decode_ms_tm.cu)
+    static_assert(M % NT == 0 && NT % 32 == 0 && Q % 32 == 0, "whole warps per quarter");
+    static_assert(SYW <= NT && NCOL - 2 <= 16, "one thread per syndrome word; packed hard bits fit");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *msg = reinterpret_cast<T *>(smem_raw);                                   // [NP][M], check order
+    uint32_t *hb = reinterpret_cast<uint32_t *>(smem_raw + sizeof(T) * NP * M);   // [HBW] packed hard decisions
+    __shared__ unsigned long long s_frame;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    // variable-side address of every pi_k block: check element (q, x) <-> variable element
+    // ((theta + q) mod 4, (phi_q + x) mod Q)  (reference src/codes/mod.rs:312-322), inverted here
+    int paddr[NP > 0 ? NP : 1][EPT];
+#pragma unroll
+    for (int ei = 0; ei < EPT; ei++) {
+        const int e = tid + ei * NT, qv = e / Q, xv = e % Q;
+        static_for<0, NB>([&](auto bi) {
+            constexpr int b = decltype(bi)::value;
+            if constexpr (P::blk(b).isp) {
+                constexpr int ps = count_p<P>(b);
+                const int q = (qv - (int)prm.theta[b]) & 3;
+                const int x = (xv - (int)prm.phi[b][q]) & (Q - 1);
+                paddr[ps][ei] = ps * M + q * Q + x;
+            }
+        });
+    }
+
+    for (;;) {
+        if (tid == 0) s_frame = atomicAdd(counter, 1ull);
+        __syncthreads();
+        const unsigned long long frame = s_frame;
+        if (frame >= batch) break;
+        const T *llr = llrs_all + frame * (unsigned long long)N;
+
+        // zero-initialised state, every call (:368, :374)
+        T Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[NB][EPT];
+#pragma unroll
+        for (int ei = 0; ei < EPT; ei++) {
+            const int e = tid + ei * NT;
+#pragma unroll
+            for (int c = 0; c < NCOL; c++) Lv[c][ei] = c < NCOL - 1 ? llr[c * M + e] : A::zero();   // :382-383
+#pragma unroll
+            for (int i = 0; i < NI; i++) idm[i][ei] = A::zero();
+#pragma unroll
+            for (int b = 0; b < NB; b++) vold[b][ei] = A::zero();
+#pragma unroll
+            for (int p = 0; p < NP; p++) msg[p * M + e] = A::zero();
+        }
+        for (int i = tid; i < HBW; i += NT) hb[i] = 0;
+        __syncthreads();
+
+        unsigned iters_run = max_iters;
+        bool ok = false, hb_complete = true;
+        uint32_t pack[EPT];
+        auto flush_pack = [&]() {      // ballot-pack the hard bits of the columns stage 1 skipped
+#pragma unroll
+            for (int ei = 0; ei < EPT; ei++) {
+                int kpos = 0;
+                static_for<0, NCOL>([&](auto ci) {
+                    constexpr int c = NCOL - 1 - decltype(ci)::value;
+                    if constexpr (c != CA && c != CP) {
+                        const unsigned bw = __ballot_sync(0xFFFFFFFFu, (pack[ei] >> kpos) & 1u);
+                        if (lane == 0) hb[(c * M + tid + ei * NT) >> 5] = bw;
+                        kpos++;
+                    }
+                });
+            }
+        };
+
+        for (unsigned iter = 0; iter < max_iters; iter++) {
+            // ================= variable phase =================
+#pragma unroll
+            for (int ei = 0; ei < EPT; ei++) {
+                pack[ei] = 0;
+                static_for<0, NCOL>([&](auto ci) {
+                    constexpr int c = decltype(ci)::value;
+                    T va = Lv[c][ei];
+                    T ub[6];
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).col == c) {
+                            constexpr int k = pos_in_col<P>(b);
+                            T u;
+                            if constexpr (P::blk(b).isp) u = msg[paddr[count_p<P>(b)][ei]];
+                            else u = idm[count_i<P>(b)][ei];
+                            ub[k] = u;
+                            va = A::sat_add(va, u);                                   // :408, ascending idx
+                        }
+                    });
+                    const bool hard = A::hard_bit(va);
+                    if constexpr (c == CA || c == CP) {
+                        const unsigned bw = __ballot_sync(0xFFFFFFFFu, hard);
+                        if (lane == 0) hb[(c * M + tid + ei * NT) >> 5] = bw;
+                    } else {
+                        pack[ei] = pack[ei] * 2u + (hard ? 1u : 0u);
+                    }
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).col == c) {
+                            constexpr int k = pos_in_col<P>(b);
+                            const T nv = A::sat_sub(va, ub[k]);                       // :421
+                            if constexpr (P::blk(b).isp) msg[paddr[count_p<P>(b)][ei]] = nv;
+                            else idm[count_i<P>(b)][ei] = nv;
+                        }
+                    });
+                });
+            }
+            __syncthreads();
+
+            // ================= check phase =================
+#pragma unroll
+            for (int ei = 0; ei < EPT; ei++) {
+                const int e = tid + ei * NT;
+                static_for<0, NROW>([&](auto ri) {
+                    constexpr int r = decltype(ri)::value;
+                    constexpr int DC = row_degree<P>(r);
+                    T a[kMaxDegW], suf[kMaxDegW];
+                    bool sg[kMaxDegW];
+                    bool stot = false;
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).row == r) {
+                            constexpr int k = pos_in_row<P>(b);
+                            T nv;
+                            if constexpr (P::blk(b).isp) nv = msg[count_p<P>(b) * M + e];
+                            else nv = idm[count_i<P>(b)][ei];
+                            const T vo = vold[b][ei];
+                            const bool keep = (A::hard_bit(nv) == A::hard_bit(vo)) || (vo == A::zero());
+                            const T v = keep ? nv : A::zero();                        // :422-426
+                            vold[b][ei] = v;
+                            a[k] = A::abs(v);
+                            sg[k] = A::hard_bit(v);
+                            stot ^= sg[k];                                            // :439-441
+                        }
+                    });
+                    // min over the other edges = (|v| == min1 ? min2 : min1)  (:391-395)
+                    suf[DC - 1] = a[DC - 1];
+#pragma unroll
+                    for (int k = DC - 2; k >= 1; k--) suf[k] = a[k] < suf[k + 1] ? a[k] : suf[k + 1];
+                    T pre = a[0];
+                    static_for<0, NB>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        if constexpr (P::blk(b).row == r) {
+                            constexpr int k = pos_in_row<P>(b);
+                            T mu;
+                            if constexpr (k == 0) mu = suf[1];
+                            else if constexpr (k == DC - 1) mu = pre;
+                            else mu = pre < suf[k + 1] ? pre : suf[k + 1];
+                            if constexpr (k > 0 && k < DC - 1) pre = pre < a[k] ? pre : a[k];
+                            T u = mu;
+                            if (stot != sg[k]) u = A::neg(u);                          // :398-405
+                            if constexpr (P::blk(b).isp) msg[count_p<P>(b) * M + e] = u;
+                            else idm[count_i<P>(b)][ei] = u;
+                        }
+                    });
+                });
+            }
+            // ---- parity of the marginals' hard bits (:445-453): two-stage, bit-packed ----
+            auto syndrome_word = [&](int sw) {
+                uint32_t synd = 0;
+                const int i0 = (sw * 32) % M, r = (sw * 32) / M;
+                const int q = i0 / Q, iq0 = i0 % Q;
+                static_for<0, NB>([&](auto bi) {
+                    constexpr int b = decltype(bi)::value;
+                    if (P::blk(b).row == r) {
+                        constexpr int col = P::blk(b).col;
+                        if constexpr (P::blk(b).isp) {
+                            const int qv = ((int)prm.theta[b] + q) & 3;
+                            const int s = ((int)prm.phi[b][q] + iq0) & (Q - 1);
+                            const int base = (col * M + qv * Q) >> 5;
+                            const int w0 = s >> 5, w1 = (w0 + 1) & (Q / 32 - 1);
+                            synd ^= __funnelshift_r(hb[base + w0], hb[base + w1], s & 31);
+                        } else {
+                            synd ^= hb[(col * M + i0) >> 5];
+                        }
+                    }
+                });
+                return synd;
+            };
+            uint32_t synd = 0;
+            if (tid >= NT - M / 32) synd = syndrome_word(tid - (NT - M / 32));
+            hb_complete = false;
+            if (__syncthreads_or(synd != 0) == 0) {
+                flush_pack();
+                hb_complete = true;
+                __syncthreads();
+                synd = 0;
+                for (int sw = M / 32 + tid; sw < SYW; sw += NT) synd |= syndrome_word(sw);
+                if (__syncthreads_or(synd != 0) == 0) {
+                    ok = true;
+                    iters_run = iter;                                                 // :462
+                    break;
+                }
+            }
+        }
+        if (!hb_complete) {
+            flush_pack();
+            __syncthreads();
+        }
+
+        // output: hard decisions of all n+p marginals, MSB first (:455-461, :466-473)
+        uint8_t *out = out_all + frame * (unsigned long long)(NV / 8);
+        const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+        for (int i = tid; i < HBW; i += NT) {
+            const uint32_t rev = __brev(hb[i]);
+            if (aligned) {
+                reinterpret_cast<uint32_t *>(out)[i] = __byte_perm(rev, 0, 0x0123);
+            } else {
+                out[4 * i + 0] = (uint8_t)(rev >> 24); out[4 * i + 1] = (uint8_t)(rev >> 16);
+                out[4 * i + 2] = (uint8_t)(rev >> 8);  out[4 * i + 3] = (uint8_t)rev;
+            }
+        }
+        if (tid == 0) {
+            if (success) success[frame] = ok ? 1 : 0;
+            if (iters_out) iters_out[frame] = iters_run;
+        }
+        __syncthreads();
+    }
+}
+
+template <int RATE, int M, class T, int NT>
+cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+                        size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    typedef Proto<RATE> P;
+    constexpr int NP = count_p<P>(P::NB);
+    const TmParams prm = make_params<RATE>(c);
+    const size_t smem = sizeof(T) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32;
+    auto kern = decode_ms_tm_wide_kernel<RATE, M, T, NT>;
+    static bool configured[16] = {};
+    if (!configured[ctx.device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[ctx.device & 15] = true;
+    }
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
+    if (grid > batch) grid = batch;
+    unsigned long long *counter = nullptr;
+    e = next_counter(ctx.device, stream, &counter);
+    if (e != cudaSuccess) return e;
+    const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
+    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, static_cast<const T *>(llrs), output, (unsigned long long)batch,
+                                                mi, success, iters, counter);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int RATE, int M, int NT, bool WITH_I8>
+bool dispatch_type(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *llrs, uint8_t *output,
+                   size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                   cudaError_t *err) {
+    switch (llr_type) {
+        case kI8:
+            if constexpr (WITH_I8) {
+                *err = launch_wide<RATE, M, int8_t, NT>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
+                return true;
+            } else {
+                return false;
+            }
+        case kI16:
+            *err = launch_wide<RATE, M, int16_t, NT>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
+            return true;
+        case kI32:
+            *err = launch_wide<RATE, M, int32_t, NT>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
+            return true;
+        case kF32:
+            *err = launch_wide<RATE, M, float, NT>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
+            return true;
+        default:
+            return false;      // f64 stays on the generic kernel
+    }
+}
+
+}  // namespace
+
+// Returns true (and launches) if the wide-lane TM kernel covers (code, llr_type).
+bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
+                              size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                              cudaError_t *err) {
+    const CodeInfo &c = *code_info(code);
+    switch (code) {
+        case 3:   // TM1280: every type (M = 128 is too small for the packed i8 kernel)
+            if (!structure_matches<2>(c) || c.m != 128) return false;
+            return dispatch_type<2, 128, 128, true>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 4:
+            if (!structure_matches<1>(c) || c.m != 256) return false;
+            return dispatch_type<1, 256, 256, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 5:
+            if (!structure_matches<0>(c) || c.m != 512) return false;
+            return dispatch_type<0, 512, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 6:
+            if (!structure_matches<2>(c) || c.m != 512) return false;
+            return dispatch_type<2, 512, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 7:
+            if (!structure_matches<1>(c) || c.m != 1024) return false;
+            return dispatch_type<1, 1024, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 8:
+            if (!structure_matches<0>(c) || c.m != 2048) return false;
+            return dispatch_type<0, 2048, 1024, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        default:
+            return false;
+    }
+}
+
+bool has_decode_ms_tm_wide(int code, int llr_type) {
+    if (code < 3 || code > 8) return false;
+    if (llr_type == kF64) return false;
+    if (llr_type == kI8) return code == 3;
+    return true;
+}
+
+}  // namespace ldpc

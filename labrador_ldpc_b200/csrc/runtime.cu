@@ -25,6 +25,10 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
                             cudaError_t *err);
 bool has_decode_ms_tm_i8(int code);
+bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
+                              size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                              cudaError_t *err);
+bool has_decode_ms_tm_wide(int code, int llr_type);
 
 namespace {
 
@@ -240,11 +244,20 @@ cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void 
         cudaError_t err = cudaSuccess;
         if (launch_decode_ms_tm_i8(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err)) return err;
     }
+    if (!force_generic()) {
+        cudaError_t err = cudaSuccess;
+        if (launch_decode_ms_tm_wide(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err))
+            return err;
+    }
     return launch_decode_ms_generic(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream);
 }
 
 const char *decode_ms_kernel_name(int code, int llr_type) {
     if (llr_type == kI8 && has_decode_ms_tm_i8(code) && !force_generic()) return "ms_tm_s16x2<i8>";
+    if (has_decode_ms_tm_wide(code, llr_type) && !force_generic()) {
+        static const char *wide[kNumLlrTypes] = {"ms_tm_wide<i8>", "ms_tm_wide<i16>", "ms_tm_wide<i32>", "ms_tm_wide<f32>", ""};
+        return wide[llr_type];
+    }
     static const char *names[kNumLlrTypes] = {"ms_generic<i8>", "ms_generic<i16>", "ms_generic<i32>",
                                               "ms_generic<f32>", "ms_generic<f64>"};
     if (llr_type < 0 || llr_type >= kNumLlrTypes) return "invalid";
