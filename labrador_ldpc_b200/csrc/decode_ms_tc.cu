@@ -1,0 +1,279 @@
+// Min-sum decoder for the TC codes (TC128 / TC256 / TC512), any LLR type: codewords per WARP.
+//
+// Replaces LDPCCode::decode_ms::<T> (reference src/decoder.rs:347-475) for the three telecommand
+// codes.  Their parity-check matrix is a 4 x 8 array of M x M rotated identities (M = n/8 = 16, 32,
+// 64; four cells hold the sum of two), 32 blocks, check degree 8, variable degree 5 or 3
+// (reference src/codes/compact_parity_checks.rs:21-78, block order of src/codes/mod.rs:295-361).
+//
+// A group of G = min(M, 32) lanes decodes one codeword: lane s owns element s (and s+32 for M = 64)
+// of every prototype column (variable side) and every prototype row (check side).  TC128 packs two
+// codewords into one warp.  Messages live in a per-warp slice of shared memory in check order
+// (the variable side reads/writes element (j - shift) mod M of the block), the two phases of an
+// iteration are separated by __syncwarp() only -- no CTA barrier anywhere -- and every warp pulls
+// its next codewords from an atomic counter, so early exits of one warp never stall another.
+// Arithmetic: the scalar DecodeFrom semantics of llr_arith.cuh; saturating adds in ascending edge
+// index per variable (:408); self-correction against the previous v kept in registers (:422-426);
+// min over the other edges by prefix/suffix minima (= min1/min2 selection, :391-395).
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "llr_arith.cuh"
+#include "runtime.h"
+
+namespace ldpc {
+namespace tm { cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **out); }
+
+namespace {
+
+struct TcBlk { int row, col; };
+// block positions shared by the three TC prototypes, in the reference iterator's order
+__host__ __device__ constexpr TcBlk tc_blk(int b) {
+    constexpr TcBlk t[32] = {{0, 0}, {0, 0}, {0, 1}, {0, 2}, {0, 3}, {0, 5}, {0, 6}, {0, 7},
+                             {1, 0}, {1, 1}, {1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 6}, {1, 7},
+                             {2, 0}, {2, 1}, {2, 2}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 7},
+                             {3, 0}, {3, 1}, {3, 2}, {3, 3}, {3, 3}, {3, 4}, {3, 5}, {3, 6}};
+    return t[b];
+}
+__host__ __device__ constexpr int tc_pos_in_col(int b) {
+    int c = 0;
+    for (int i = 0; i < b; i++) c += tc_blk(i).col == tc_blk(b).col;
+    return c;
+}
+__host__ __device__ constexpr int tc_pos_in_row(int b) { return b % 8; }
+
+template <int I, int N, class F> __device__ __forceinline__ void tc_static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        tc_static_for<I + 1, N>(f);
+    }
+}
+
+struct TcParams { uint8_t shift[32]; };
+
+constexpr int kWarpsPerCta = 4;
+
+template <int M, class T>
+__global__ void __launch_bounds__(32 * kWarpsPerCta)
+decode_ms_tc_kernel(const TcParams prm, const T *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
+                    unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
+                    uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+    typedef Arith<T> A;
+    typedef typename MsgStore<T>::type ST;          // shared-memory storage type of a message
+    typedef typename A::C CT;                       // register (compute) type
+    constexpr int EPT = M > 32 ? M / 32 : 1;        // elements per lane
+    constexpr int G = M / EPT;                       // lanes per codeword
+    constexpr int CWW = 32 / G;                      // codewords per warp
+    constexpr int N = 8 * M, NC = 4 * M, E = 32 * M;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cwl = lane / G, sl = lane % G;
+    // per-warp slice: messages [CWW][32][M] of T, then hard bits [CWW][N] bytes
+    constexpr size_t kWarpBytes = sizeof(ST) * CWW * E + (size_t)CWW * N;
+    unsigned char *wbase = smem_raw + (size_t)warp * ((kWarpBytes + 15) & ~(size_t)15);
+    ST *msg = reinterpret_cast<ST *>(wbase) + (size_t)cwl * E;
+    uint8_t *hbv = wbase + sizeof(ST) * CWW * E + (size_t)cwl * N;
+    const unsigned group_mask = (G == 32 ? kFull : ((1u << G) - 1u)) << (cwl * G);
+
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)CWW);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= batch) break;
+        const unsigned long long frame = base + cwl;
+        const bool live = frame < batch;                 // the second codeword of a TC128 warp may not exist
+        const T *llr = llrs_all + (live ? frame : base) * (unsigned long long)N;
+
+        CT Lv[8][EPT], vold[32][EPT];
+#pragma unroll
+        for (int ei = 0; ei < EPT; ei++) {
+            const int e = sl + ei * G;
+#pragma unroll
+            for (int c = 0; c < 8; c++) Lv[c][ei] = (CT)llr[c * M + e];
+#pragma unroll
+            for (int b = 0; b < 32; b++) { vold[b][ei] = A::zero(); msg[b * M + e] = (ST)A::zero(); }
+#pragma unroll
+            for (int c = 0; c < 8; c++) hbv[c * M + e] = 0;
+        }
+        __syncwarp();
+
+        bool done = !live;           // this lane group's codeword is finished (or absent)
+        bool ok = false;
+        unsigned iters_run = max_iters;
+        for (unsigned iter = 0; iter < max_iters; iter++) {
+            // ---- variable phase ----
+            if (!done) {
+#pragma unroll
+                for (int ei = 0; ei < EPT; ei++) {
+                    const int j = sl + ei * G;
+                    tc_static_for<0, 8>([&](auto ci) {
+                        constexpr int c = decltype(ci)::value;
+                        CT va = Lv[c][ei];
+                        CT ub[5];
+                        tc_static_for<0, 32>([&](auto bi) {
+                            constexpr int b = decltype(bi)::value;
+                            if constexpr (tc_blk(b).col == c) {
+                                const int i = (j - (int)prm.shift[b]) & (M - 1);
+                                const CT u = (CT)msg[b * M + i];
+                                ub[tc_pos_in_col(b)] = u;
+                                va = A::sat_add(va, u);                                  // :408
+                            }
+                        });
+                        hbv[c * M + j] = A::hard_bit(va) ? 1 : 0;
+                        tc_static_for<0, 32>([&](auto bi) {
+                            constexpr int b = decltype(bi)::value;
+                            if constexpr (tc_blk(b).col == c) {
+                                const int i = (j - (int)prm.shift[b]) & (M - 1);
+                                msg[b * M + i] = (ST)A::sat_sub(va, ub[tc_pos_in_col(b)]);   // :421
+                            }
+                        });
+                    });
+                }
+            }
+            __syncwarp();
+            // ---- check phase ----
+            bool par_any = false;
+            if (!done) {
+#pragma unroll
+                for (int ei = 0; ei < EPT; ei++) {
+                    const int i = sl + ei * G;
+                    tc_static_for<0, 4>([&](auto ri) {
+                        constexpr int r = decltype(ri)::value;
+                        CT a[8], suf[8];
+                        bool sg[8];
+                        bool stot = false;
+                        int par = 0;
+                        tc_static_for<0, 8>([&](auto ki) {
+                            constexpr int k = decltype(ki)::value;
+                            constexpr int b = r * 8 + k;
+                            const CT nv = (CT)msg[b * M + i];
+                            const CT vo = vold[b][ei];
+                            const bool keep = (A::hard_bit(nv) == A::hard_bit(vo)) || (vo == A::zero());
+                            const CT v = keep ? nv : A::zero();                           // :422-426
+                            vold[b][ei] = v;
+                            a[k] = A::abs(v);
+                            sg[k] = A::hard_bit(v);
+                            stot ^= sg[k];
+                            par ^= hbv[tc_blk(b).col * M + ((i + (int)prm.shift[b]) & (M - 1))];   // :445-447
+                        });
+                        par_any |= par != 0;
+                        suf[7] = a[7];
+#pragma unroll
+                        for (int k = 6; k >= 1; k--) suf[k] = a[k] < suf[k + 1] ? a[k] : suf[k + 1];
+                        CT pre = a[0];
+                        tc_static_for<0, 8>([&](auto ki) {
+                            constexpr int k = decltype(ki)::value;
+                            constexpr int b = r * 8 + k;
+                            CT mu;
+                            if constexpr (k == 0) mu = suf[1];
+                            else if constexpr (k == 7) mu = pre;
+                            else mu = pre < suf[k + 1] ? pre : suf[k + 1];
+                            if constexpr (k > 0 && k < 7) pre = pre < a[k] ? pre : a[k];
+                            if (stot != sg[k]) mu = A::neg(mu);                           // :398-405
+                            msg[b * M + i] = (ST)mu;
+                        });
+                    });
+                }
+            }
+            const unsigned bad = __ballot_sync(kFull, par_any);
+            if (!done && (bad & group_mask) == 0) {                                       // :453
+                done = true; ok = true; iters_run = iter;                                 // :462
+            }
+            __syncwarp();
+            if (__all_sync(kFull, done)) break;
+        }
+
+        // ---- output: hard decisions MSB first (:455-461, :466-473); p = 0 for TC codes ----
+        if (live) {
+            uint8_t *out = out_all + frame * (unsigned long long)(N / 8);
+            for (int o = sl; o < N / 8; o += G) {
+                unsigned byte = 0;
+#pragma unroll
+                for (int bit = 0; bit < 8; bit++) byte |= (unsigned)hbv[o * 8 + bit] << (7 - bit);
+                out[o] = (uint8_t)byte;
+            }
+            if (sl == 0) {
+                if (success) success[frame] = ok ? 1 : 0;
+                if (iters_out) iters_out[frame] = iters_run;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int M, class T>
+cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
+    TcParams prm{};
+    for (int b = 0; b < 32; b++) prm.shift[b] = (uint8_t)c.blocks[b].shift;
+    const size_t warp_bytes = ((sizeof(typename MsgStore<T>::type) * CWW * 32 * M + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
+    const size_t smem = warp_bytes * kWarpsPerCta;
+    auto kern = decode_ms_tc_kernel<M, T>;
+    static bool configured[16] = {};
+    if (!configured[ctx.device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[ctx.device & 15] = true;
+    }
+    int per_sm = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kWarpsPerCta, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long groups = (batch + CWW - 1) / CWW;
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
+    const unsigned long long need = (groups + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > need) grid = need;
+    unsigned long long *counter = nullptr;
+    e = tm::next_counter(ctx.device, stream, &counter);
+    if (e != cudaSuccess) return e;
+    const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
+    kern<<<(unsigned)grid, 32 * kWarpsPerCta, smem, stream>>>(prm, static_cast<const T *>(llrs), output,
+                                                               (unsigned long long)batch, mi, success, iters, counter);
+    count_launch();
+    return cudaGetLastError();
+}
+
+bool tc_structure_matches(const CodeInfo &c) {
+    if (c.n_blocks != 32 || c.rows != 4 || c.cols != 8 || c.p != 0) return false;
+    for (int b = 0; b < 32; b++) {
+        const Block &blk = c.blocks[b];
+        if (blk.kind != kIdentity || blk.row != tc_blk(b).row || blk.col != tc_blk(b).col) return false;
+        if (blk.edge_offset != b * c.m || blk.shift < 0 || blk.shift >= c.m) return false;
+    }
+    return true;
+}
+
+template <int M>
+bool tc_dispatch(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *llrs, uint8_t *output, size_t batch,
+                 size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err) {
+    switch (llr_type) {
+        case kI8: *err = launch_tc<M, int8_t>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
+        case kI16: *err = launch_tc<M, int16_t>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
+        case kI32: *err = launch_tc<M, int32_t>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
+        case kF32: *err = launch_tc<M, float>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
+        case kF64: *err = launch_tc<M, double>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
+        default: return false;
+    }
+}
+
+}  // namespace
+
+bool launch_decode_ms_tc(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
+                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err) {
+    if (code < 0 || code > 2) return false;
+    const CodeInfo &c = *code_info(code);
+    if (!tc_structure_matches(c)) return false;
+    switch (c.m) {
+        case 16: return tc_dispatch<16>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 32: return tc_dispatch<32>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 64: return tc_dispatch<64>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        default: return false;
+    }
+}
+
+bool has_decode_ms_tc(int code) { return code >= 0 && code <= 2; }
+
+}  // namespace ldpc

@@ -32,6 +32,8 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
                          uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
     typedef Proto<RATE> P;
     typedef Arith<T> A;
+    typedef typename MsgStore<T>::type ST;          // shared-memory storage type of a message
+    typedef typename A::C CT;                       // register (compute) type
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
     constexpr int NP = count_p<P>(NB), NI = NB - NP;
     constexpr int Q = M / 4, EPT = M / NT;
@@ -42,8 +44,8 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
     static_assert(SYW <= NT && NCOL - 2 <= 16, "one thread per syndrome word; packed hard bits fit");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *msg = reinterpret_cast<T *>(smem_raw);                                   // [NP][M], check order
-    uint32_t *hb = reinterpret_cast<uint32_t *>(smem_raw + sizeof(T) * NP * M);   // [HBW] packed hard decisions
+    ST *msg = reinterpret_cast<ST *>(smem_raw);                                 // [NP][M], check order
+    uint32_t *hb = reinterpret_cast<uint32_t *>(smem_raw + sizeof(ST) * NP * M);   // [HBW] packed hard decisions
     __shared__ unsigned long long s_frame;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -73,18 +75,18 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
         const T *llr = llrs_all + frame * (unsigned long long)N;
 
         // zero-initialised state, every call (:368, :374)
-        T Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[NB][EPT];
+        CT Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[NB][EPT];
 #pragma unroll
         for (int ei = 0; ei < EPT; ei++) {
             const int e = tid + ei * NT;
 #pragma unroll
-            for (int c = 0; c < NCOL; c++) Lv[c][ei] = c < NCOL - 1 ? llr[c * M + e] : A::zero();   // :382-383
+            for (int c = 0; c < NCOL; c++) Lv[c][ei] = c < NCOL - 1 ? (CT)llr[c * M + e] : A::zero();   // :382-383
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][ei] = A::zero();
 #pragma unroll
             for (int b = 0; b < NB; b++) vold[b][ei] = A::zero();
 #pragma unroll
-            for (int p = 0; p < NP; p++) msg[p * M + e] = A::zero();
+            for (int p = 0; p < NP; p++) msg[p * M + e] = (ST)A::zero();
         }
         for (int i = tid; i < HBW; i += NT) hb[i] = 0;
         __syncthreads();
@@ -114,14 +116,14 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
                 pack[ei] = 0;
                 static_for<0, NCOL>([&](auto ci) {
                     constexpr int c = decltype(ci)::value;
-                    T va = Lv[c][ei];
-                    T ub[6];
+                    CT va = Lv[c][ei];
+                    CT ub[6];
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).col == c) {
                             constexpr int k = pos_in_col<P>(b);
-                            T u;
-                            if constexpr (P::blk(b).isp) u = msg[paddr[count_p<P>(b)][ei]];
+                            CT u;
+                            if constexpr (P::blk(b).isp) u = (CT)msg[paddr[count_p<P>(b)][ei]];
                             else u = idm[count_i<P>(b)][ei];
                             ub[k] = u;
                             va = A::sat_add(va, u);                                   // :408, ascending idx
@@ -138,8 +140,8 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).col == c) {
                             constexpr int k = pos_in_col<P>(b);
-                            const T nv = A::sat_sub(va, ub[k]);                       // :421
-                            if constexpr (P::blk(b).isp) msg[paddr[count_p<P>(b)][ei]] = nv;
+                            const CT nv = A::sat_sub(va, ub[k]);                      // :421
+                            if constexpr (P::blk(b).isp) msg[paddr[count_p<P>(b)][ei]] = (ST)nv;
                             else idm[count_i<P>(b)][ei] = nv;
                         }
                     });
@@ -154,19 +156,19 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
                 static_for<0, NROW>([&](auto ri) {
                     constexpr int r = decltype(ri)::value;
                     constexpr int DC = row_degree<P>(r);
-                    T a[kMaxDegW], suf[kMaxDegW];
+                    CT a[kMaxDegW], suf[kMaxDegW];
                     bool sg[kMaxDegW];
                     bool stot = false;
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).row == r) {
                             constexpr int k = pos_in_row<P>(b);
-                            T nv;
-                            if constexpr (P::blk(b).isp) nv = msg[count_p<P>(b) * M + e];
+                            CT nv;
+                            if constexpr (P::blk(b).isp) nv = (CT)msg[count_p<P>(b) * M + e];
                             else nv = idm[count_i<P>(b)][ei];
-                            const T vo = vold[b][ei];
+                            const CT vo = vold[b][ei];
                             const bool keep = (A::hard_bit(nv) == A::hard_bit(vo)) || (vo == A::zero());
-                            const T v = keep ? nv : A::zero();                        // :422-426
+                            const CT v = keep ? nv : A::zero();                       // :422-426
                             vold[b][ei] = v;
                             a[k] = A::abs(v);
                             sg[k] = A::hard_bit(v);
@@ -177,19 +179,19 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
                     suf[DC - 1] = a[DC - 1];
 #pragma unroll
                     for (int k = DC - 2; k >= 1; k--) suf[k] = a[k] < suf[k + 1] ? a[k] : suf[k + 1];
-                    T pre = a[0];
+                    CT pre = a[0];
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).row == r) {
                             constexpr int k = pos_in_row<P>(b);
-                            T mu;
+                            CT mu;
                             if constexpr (k == 0) mu = suf[1];
                             else if constexpr (k == DC - 1) mu = pre;
                             else mu = pre < suf[k + 1] ? pre : suf[k + 1];
                             if constexpr (k > 0 && k < DC - 1) pre = pre < a[k] ? pre : a[k];
-                            T u = mu;
+                            CT u = mu;
                             if (stot != sg[k]) u = A::neg(u);                          // :398-405
-                            if constexpr (P::blk(b).isp) msg[count_p<P>(b) * M + e] = u;
+                            if constexpr (P::blk(b).isp) msg[count_p<P>(b) * M + e] = (ST)u;
                             else idm[count_i<P>(b)][ei] = u;
                         }
                     });
@@ -264,7 +266,7 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
     typedef Proto<RATE> P;
     constexpr int NP = count_p<P>(P::NB);
     const TmParams prm = make_params<RATE>(c);
-    const size_t smem = sizeof(T) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32;
+    const size_t smem = sizeof(typename MsgStore<T>::type) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32;
     auto kern = decode_ms_tm_wide_kernel<RATE, M, T, NT>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {

@@ -11,31 +11,42 @@ namespace ldpc {
 
 template <class T> struct Arith;
 
+// Shared-memory storage type of a message: sub-word types are widened to 32 bits so that consecutive
+// lanes hit consecutive banks (byte / half-word accesses serialise four / two lanes per bank).
+template <class T> struct MsgStore { typedef T type; };
+template <> struct MsgStore<int8_t> { typedef int32_t type; };
+template <> struct MsgStore<int16_t> { typedef int32_t type; };
+
+// i8 / i16 compute in 32-bit registers (type C = int): values are sign-extended once when loaded and every
+// operation re-clamps to the narrow range, so no per-operation sign-extension instructions are needed.
 template <> struct Arith<int8_t> {
+    typedef int C;
     static constexpr const char *name = "i8";
-    __device__ static __forceinline__ int8_t zero() { return 0; }
-    __device__ static __forceinline__ int8_t one() { return 1; }
-    __device__ static __forceinline__ int8_t maxval() { return INT8_MAX; }
-    __device__ static __forceinline__ int8_t abs(int8_t x) { return (int8_t)min(::abs((int)x), 127); }
-    __device__ static __forceinline__ int8_t sat_add(int8_t a, int8_t b) { return (int8_t)max(-128, min(127, (int)a + (int)b)); }
-    __device__ static __forceinline__ int8_t sat_sub(int8_t a, int8_t b) { return (int8_t)max(-128, min(127, (int)a - (int)b)); }
-    __device__ static __forceinline__ int8_t neg(int8_t x) { return (int8_t)(-(int)x); }
-    __device__ static __forceinline__ bool hard_bit(int8_t x) { return x < 0; }
+    __device__ static __forceinline__ int zero() { return 0; }
+    __device__ static __forceinline__ int one() { return 1; }
+    __device__ static __forceinline__ int maxval() { return INT8_MAX; }
+    __device__ static __forceinline__ int abs(int x) { return min(::abs(x), 127); }
+    __device__ static __forceinline__ int sat_add(int a, int b) { return max(__viaddmin_s32(a, b, 127), -128); }
+    __device__ static __forceinline__ int sat_sub(int a, int b) { return max(__viaddmin_s32(a, -b, 127), -128); }
+    __device__ static __forceinline__ int neg(int x) { return -x; }
+    __device__ static __forceinline__ bool hard_bit(int x) { return x < 0; }
 };
 
 template <> struct Arith<int16_t> {
+    typedef int C;
     static constexpr const char *name = "i16";
-    __device__ static __forceinline__ int16_t zero() { return 0; }
-    __device__ static __forceinline__ int16_t one() { return 1; }
-    __device__ static __forceinline__ int16_t maxval() { return INT16_MAX; }
-    __device__ static __forceinline__ int16_t abs(int16_t x) { return (int16_t)min(::abs((int)x), 32767); }
-    __device__ static __forceinline__ int16_t sat_add(int16_t a, int16_t b) { return (int16_t)max(-32768, min(32767, (int)a + (int)b)); }
-    __device__ static __forceinline__ int16_t sat_sub(int16_t a, int16_t b) { return (int16_t)max(-32768, min(32767, (int)a - (int)b)); }
-    __device__ static __forceinline__ int16_t neg(int16_t x) { return (int16_t)(-(int)x); }
-    __device__ static __forceinline__ bool hard_bit(int16_t x) { return x < 0; }
+    __device__ static __forceinline__ int zero() { return 0; }
+    __device__ static __forceinline__ int one() { return 1; }
+    __device__ static __forceinline__ int maxval() { return INT16_MAX; }
+    __device__ static __forceinline__ int abs(int x) { return min(::abs(x), 32767); }
+    __device__ static __forceinline__ int sat_add(int a, int b) { return max(__viaddmin_s32(a, b, 32767), -32768); }
+    __device__ static __forceinline__ int sat_sub(int a, int b) { return max(__viaddmin_s32(a, -b, 32767), -32768); }
+    __device__ static __forceinline__ int neg(int x) { return -x; }
+    __device__ static __forceinline__ bool hard_bit(int x) { return x < 0; }
 };
 
 template <> struct Arith<int32_t> {
+    typedef int32_t C;
     static constexpr const char *name = "i32";
     __device__ static __forceinline__ int32_t zero() { return 0; }
     __device__ static __forceinline__ int32_t one() { return 1; }
@@ -51,6 +62,7 @@ template <> struct Arith<int32_t> {
 };
 
 template <> struct Arith<float> {
+    typedef float C;
     static constexpr const char *name = "f32";
     __device__ static __forceinline__ float zero() { return 0.0f; }
     __device__ static __forceinline__ float one() { return 1.0f; }
@@ -63,6 +75,7 @@ template <> struct Arith<float> {
 };
 
 template <> struct Arith<double> {
+    typedef double C;
     static constexpr const char *name = "f64";
     __device__ static __forceinline__ double zero() { return 0.0; }
     __device__ static __forceinline__ double one() { return 1.0; }

@@ -29,6 +29,9 @@ bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void
                               size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
                               cudaError_t *err);
 bool has_decode_ms_tm_wide(int code, int llr_type);
+bool launch_decode_ms_tc(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
+                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err);
+bool has_decode_ms_tc(int code);
 
 namespace {
 
@@ -248,6 +251,8 @@ cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void 
         cudaError_t err = cudaSuccess;
         if (launch_decode_ms_tm_wide(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err))
             return err;
+        if (launch_decode_ms_tc(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err))
+            return err;
     }
     return launch_decode_ms_generic(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream);
 }
@@ -257,6 +262,10 @@ const char *decode_ms_kernel_name(int code, int llr_type) {
     if (has_decode_ms_tm_wide(code, llr_type) && !force_generic()) {
         static const char *wide[kNumLlrTypes] = {"ms_tm_wide<i8>", "ms_tm_wide<i16>", "ms_tm_wide<i32>", "ms_tm_wide<f32>", ""};
         return wide[llr_type];
+    }
+    if (has_decode_ms_tc(code) && !force_generic() && llr_type >= 0 && llr_type < kNumLlrTypes) {
+        static const char *tc[kNumLlrTypes] = {"ms_tc_warp<i8>", "ms_tc_warp<i16>", "ms_tc_warp<i32>", "ms_tc_warp<f32>", "ms_tc_warp<f64>"};
+        return tc[llr_type];
     }
     static const char *names[kNumLlrTypes] = {"ms_generic<i8>", "ms_generic<i16>", "ms_generic<i32>",
                                               "ms_generic<f32>", "ms_generic<f64>"};
