@@ -13,9 +13,15 @@
 // that behaviour is reproduced here (one pass, erasure_iters = 0).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "runtime.h"
 
 namespace ldpc {
+
+bool launch_decode_bf_tm(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
+                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err);
+
 namespace {
 
 __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restrict__ in_all,
@@ -120,6 +126,13 @@ __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restric
 
 cudaError_t launch_decode_bf(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
                              size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    if (batch == 0) return cudaSuccess;
+    {   // TM codes: bit-packed warp-per-codeword kernel (LABRADOR_LDPC_FORCE_GENERIC=1 keeps the table-driven one)
+        static const bool generic = [] { const char *e = getenv("LABRADOR_LDPC_FORCE_GENERIC"); return e && e[0] == '1'; }();
+        cudaError_t err = cudaSuccess;
+        if (!generic && launch_decode_bf_tm(ctx, code, input, output, batch, max_iters, success, iters, stream, &err))
+            return err;
+    }
     const DeviceCode &dc = ctx.codes[code];
     const size_t smem = (size_t)dc.vars * 2 + dc.checks;
     int threads = dc.vars < 512 ? ((dc.vars + 31) / 32) * 32 : 512;
