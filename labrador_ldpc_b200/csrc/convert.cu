@@ -13,55 +13,72 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// One thread per input byte: eight LLRs written as one or more 16-byte stores.
+// One thread per 16 output bytes (16 / sizeof(T) LLRs), so every store instruction of a warp covers 512
+// contiguous bytes; unaligned caller buffers take the element-wise path.
 template <class T>
 __global__ void hard_to_llrs_kernel(const uint8_t *__restrict__ in, T *__restrict__ out,
-                                    unsigned long long n_bytes) {
+                                    unsigned long long n_llrs, const bool vec_ok) {
+    constexpr int ELEMS = 16 / sizeof(T);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += stride) {
-        const unsigned byte = in[i];
-        __align__(16) T vals[8];
+    const unsigned long long n_chunks = n_llrs / ELEMS;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_chunks; j += stride) {
+        const unsigned long long e0 = j * ELEMS;
+        unsigned bitsrc = in[e0 >> 3];
+        if constexpr (ELEMS == 16) bitsrc = (bitsrc << 8) | in[(e0 >> 3) + 1];
+        __align__(16) T vals[ELEMS];
 #pragma unroll
-        for (int b = 0; b < 8; b++)
-            vals[b] = ((byte >> (7 - b)) & 1) ? Arith<T>::neg(Arith<T>::one()) : Arith<T>::one();
-        T *dst = out + i * 8;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (sizeof(T) * 8) % 16 == 0) {
-            const uint4 *src4 = reinterpret_cast<const uint4 *>(vals);
-#pragma unroll
-            for (unsigned q = 0; q < sizeof(T) * 8 / 16; q++) reinterpret_cast<uint4 *>(dst)[q] = src4[q];
-        } else if ((reinterpret_cast<uintptr_t>(dst) & 7u) == 0 && sizeof(T) == 1) {
-            *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(vals);
+        for (int b = 0; b < ELEMS; b++) {
+            const int pos = ELEMS == 16 ? (15 - b) : (7 - (int)(e0 & 7) - b);       // MSB first within each byte
+            vals[b] = (T)(((bitsrc >> pos) & 1) ? Arith<T>::neg(Arith<T>::one()) : Arith<T>::one());
+        }
+        T *dst = out + e0;
+        if (vec_ok) {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(vals);
         } else {
 #pragma unroll
-            for (int b = 0; b < 8; b++) dst[b] = vals[b];
+            for (int b = 0; b < ELEMS; b++) dst[b] = vals[b];
         }
     }
 }
 
-// One thread per LLR; a warp ballot packs 32 hard bits, lanes 0..3 store one byte each.
+// One thread per output byte: eight consecutive LLRs are fetched with 8- or 16-byte loads (when the
+// caller's buffer is aligned), so a warp reads 32 * 8 * sizeof(T) contiguous bytes and writes 32.
 template <class T>
 __global__ void llrs_to_hard_kernel(const T *__restrict__ in, uint8_t *__restrict__ out,
-                                    unsigned long long n_llrs) {
+                                    unsigned long long n_bytes, const bool vec_ok) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const int lane = threadIdx.x & 31;
-    // n_llrs is a multiple of 128, so whole warps are either in or out of range
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_llrs; i += stride) {
-        const bool bit = Arith<T>::hard_bit(in[i]);
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, bit);
-        if (lane < 4) {
-            const unsigned byte = __brev((m >> (8 * lane)) & 0xFFu) >> 24;
-            out[((i - lane) >> 3) + lane] = (uint8_t)byte;   // warp base is a multiple of 32 LLRs = 4 bytes
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += stride) {
+        __align__(16) T vals[8];
+        const T *src = in + i * 8;
+        if (vec_ok) {
+            if constexpr (sizeof(T) == 1) {
+                *reinterpret_cast<uint2 *>(vals) = __ldg(reinterpret_cast<const uint2 *>(src));
+            } else {
+#pragma unroll
+                for (unsigned q = 0; q < sizeof(T) * 8 / 16; q++)
+                    reinterpret_cast<uint4 *>(vals)[q] = __ldg(reinterpret_cast<const uint4 *>(src) + q);
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; b++) vals[b] = src[b];
         }
+        unsigned byte = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++) byte |= (Arith<T>::hard_bit(vals[b]) ? 1u : 0u) << (7 - b);
+        out[i] = (uint8_t)byte;
     }
 }
 
 template <class T>
 cudaError_t h2l(DeviceCtx &ctx, const uint8_t *in, void *out, unsigned long long n_bytes, cudaStream_t s) {
     if (n_bytes == 0) return cudaSuccess;
-    unsigned long long blocks = (n_bytes + kThreads - 1) / kThreads;
-    const unsigned long long cap = (unsigned long long)ctx.sm_count * 16;
+    const unsigned long long n_llrs = n_bytes * 8;
+    const unsigned long long n_chunks = n_llrs / (16 / sizeof(T));
+    unsigned long long blocks = (n_chunks + kThreads - 1) / kThreads;
+    const unsigned long long cap = (unsigned long long)ctx.sm_count * 32;
     if (blocks > cap) blocks = cap;
-    hard_to_llrs_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(in, static_cast<T *>(out), n_bytes);
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    hard_to_llrs_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(in, static_cast<T *>(out), n_llrs, vec_ok);
     count_launch();
     return cudaGetLastError();
 }
@@ -69,10 +86,12 @@ cudaError_t h2l(DeviceCtx &ctx, const uint8_t *in, void *out, unsigned long long
 template <class T>
 cudaError_t l2h(DeviceCtx &ctx, const void *in, uint8_t *out, unsigned long long n_llrs, cudaStream_t s) {
     if (n_llrs == 0) return cudaSuccess;
-    unsigned long long blocks = (n_llrs + kThreads - 1) / kThreads;
-    const unsigned long long cap = (unsigned long long)ctx.sm_count * 16;
+    const unsigned long long n_bytes = n_llrs / 8;
+    unsigned long long blocks = (n_bytes + kThreads - 1) / kThreads;
+    const unsigned long long cap = (unsigned long long)ctx.sm_count * 32;
     if (blocks > cap) blocks = cap;
-    llrs_to_hard_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(static_cast<const T *>(in), out, n_llrs);
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    llrs_to_hard_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(static_cast<const T *>(in), out, n_bytes, vec_ok);
     count_launch();
     return cudaGetLastError();
 }
