@@ -311,8 +311,11 @@ bool dispatch_type(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *
         case kF32:
             *err = launch_wide<RATE, M, float, NT>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
             return true;
+        case kF64:
+            *err = launch_wide<RATE, M, double, NT>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
+            return true;
         default:
-            return false;      // f64 stays on the generic kernel
+            return false;
     }
 }
 
@@ -349,7 +352,6 @@ bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void
 
 bool has_decode_ms_tm_wide(int code, int llr_type) {
     if (code < 3 || code > 8) return false;
-    if (llr_type == kF64) return false;
     if (llr_type == kI8) return code == 3;
     return true;
 }

@@ -260,7 +260,7 @@ cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void 
 const char *decode_ms_kernel_name(int code, int llr_type) {
     if (llr_type == kI8 && has_decode_ms_tm_i8(code) && !force_generic()) return "ms_tm_s16x2<i8>";
     if (has_decode_ms_tm_wide(code, llr_type) && !force_generic()) {
-        static const char *wide[kNumLlrTypes] = {"ms_tm_wide<i8>", "ms_tm_wide<i16>", "ms_tm_wide<i32>", "ms_tm_wide<f32>", ""};
+        static const char *wide[kNumLlrTypes] = {"ms_tm_wide<i8>", "ms_tm_wide<i16>", "ms_tm_wide<i32>", "ms_tm_wide<f32>", "ms_tm_wide<f64>"};
         return wide[llr_type];
     }
     if (has_decode_ms_tc(code) && !force_generic() && llr_type >= 0 && llr_type < kNumLlrTypes) {

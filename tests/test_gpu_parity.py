@@ -404,3 +404,48 @@ def test_unaligned_device_llrs_take_plain_load_path(ldpc, oracle):
         got = c.decode_ms_batch(view, 60)
         torch.cuda.synchronize()
         assert_exact([g.cpu().numpy() for g in got], want, "batch=%d offset=%d" % (batch, off))
+
+
+def test_generic_kernels_stay_exact():
+    """Every (code, type) now has a specialised min-sum kernel; the table-driven generic kernels remain as
+    the fallback / A-B reference (LABRADOR_LDPC_FORCE_GENERIC=1) and must stay bit-exact too."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle"); sys.path.insert(0, %r + "/tests")
+import labrador_ldpc_b200 as L, pyoracle
+from frames import make_frames, hard_frames
+o = pyoracle.Oracle()
+for code, ty, eb in ((0, "i8", 3.0), (2, "f32", 2.5), (3, "i16", 3.6), (5, "i8", 1.8), (8, "i8", 1.6), (6, "f64", 3.4)):
+    c = L.LDPCCode(code)
+    assert c.decode_ms_kernel_name(ty).startswith("ms_generic"), c.decode_ms_kernel_name(ty)
+    _, _, llrs = make_frames(o, code, 48, eb, seed=31 + code, ty=ty)
+    want = o.decode_ms_batch(code, llrs, 40, nthreads=8)
+    got = c.decode_ms_batch(llrs, 40)
+    assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want)), (code, ty)
+for code in (3, 5, 8):
+    _, _, rx = hard_frames(o, code, 32, 5, seed=code)
+    want = o.decode_bf_batch(code, rx, 30)
+    got = L.LDPCCode(code).decode_bf_batch(rx, 30)
+    assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want)), code
+print("OK")
+''' % (root, root, root)
+    env = dict(os.environ, LABRADOR_LDPC_FORCE_GENERIC="1")
+    out = subprocess.check_output([sys.executable, "-c", script], env=env, text=True)
+    assert "OK" in out
+
+
+def test_specialised_kernel_dispatch(ldpc):
+    names = {(code, ty): ldpc.LDPCCode(code).decode_ms_kernel_name(ty) for code in range(9)
+             for ty in ("i8", "i16", "i32", "f32", "f64")}
+    if os.environ.get("LABRADOR_LDPC_FORCE_GENERIC") == "1":
+        pytest.skip("generic forced")
+    for (code, ty), name in names.items():
+        if code < 3:
+            assert name == "ms_tc_warp<%s>" % ty
+        elif code >= 4 and ty == "i8":
+            assert name == "ms_tm_s16x2<i8>"
+        else:
+            assert name == "ms_tm_wide<%s>" % ty
