@@ -21,7 +21,8 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["LDPCCode", "LdpcError", "lib", "LLR_TYPES", "init", "shutdown", "kernel_launch_count"]
+__all__ = ["LDPCCode", "LdpcError", "lib", "LLR_TYPES", "init", "shutdown", "kernel_launch_count",
+           "decode_ms_mixed"]
 
 _LIB_PATH = _build.LIB
 if os.path.exists(_LIB_PATH) and _build.needs_build() and os.environ.get("LABRADOR_LDPC_NO_REBUILD") != "1":
@@ -357,3 +358,21 @@ class LDPCCode(enum.IntEnum):
 
     def edge_table_crc(self):
         return int(lib.labrador_ldpc_edge_table_crc(int(self)))
+
+
+def decode_ms_mixed(jobs, maxiters):
+    """Mixed-code batch (BASELINE.json configs[3]): `jobs` is a list of (LDPCCode, llrs) with CUDA tensors.
+    Every homogeneous sub-batch is enqueued on its own CUDA stream through the `_batch_async` C entry point
+    (the kernels are specialised per code), and the caller's current stream waits for all of them.
+    Returns a list of (output, success, iters) in job order."""
+    import torch
+    results = []
+    cur = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in jobs]
+    for (code, llrs), st in zip(jobs, streams):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            results.append(code.decode_ms_batch(llrs, maxiters, stream=st.cuda_stream))
+    for st in streams:
+        cur.wait_stream(st)
+    return results

@@ -449,3 +449,18 @@ def test_specialised_kernel_dispatch(ldpc):
             assert name == "ms_tm_s16x2<i8>"
         else:
             assert name == "ms_tm_wide<%s>" % ty
+
+
+def test_mixed_code_batch_on_concurrent_streams(ldpc, oracle):
+    """BASELINE config 4: a high-rate mixed batch (TM5120 + TM6144) as two homogeneous sub-batches on
+    concurrent streams; each must match the oracle."""
+    import torch
+    jobs, wants = [], []
+    for code, eb in ((6, 3.4), (7, 2.4), (6, 4.0)):
+        _, _, llrs = make_frames(oracle, code, 96, eb, seed=70 + code, ty="i8")
+        wants.append(oracle.decode_ms_batch(code, llrs, 60, nthreads=8))
+        jobs.append((ldpc.LDPCCode(code), torch.from_numpy(llrs).cuda()))
+    results = ldpc.decode_ms_mixed(jobs, 60)
+    torch.cuda.synchronize()
+    for got, want, (code, _) in zip(results, wants, jobs):
+        assert_exact([g.cpu().numpy() for g in got], want, "mixed batch %s" % code.name)
