@@ -69,6 +69,19 @@ __global__ void llrs_to_hard_kernel(const T *__restrict__ in, uint8_t *__restric
     }
 }
 
+// i8 fast path: 16 LLRs (one 16-byte load) -> 2 output bytes; sign bits gathered with a multiply
+// ("movemask": ((w >> 7) & 0x01010101) * 0x08040201 >> 24 = the four sign bits, first byte most significant).
+__global__ void llrs_to_hard_i8x16_kernel(const uint4 *__restrict__ in, uint16_t *__restrict__ out,
+                                          unsigned long long n_chunks) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += stride) {
+        const uint4 v = __ldg(in + i);
+        auto nib = [](uint32_t w) { return (((w >> 7) & 0x01010101u) * 0x08040201u) >> 24; };
+        const uint32_t b0 = (nib(v.x) << 4) | nib(v.y), b1 = (nib(v.z) << 4) | nib(v.w);
+        out[i] = (uint16_t)(b0 | (b1 << 8));
+    }
+}
+
 template <class T>
 cudaError_t h2l(DeviceCtx &ctx, const uint8_t *in, void *out, unsigned long long n_bytes, cudaStream_t s) {
     if (n_bytes == 0) return cudaSuccess;
@@ -91,6 +104,15 @@ cudaError_t l2h(DeviceCtx &ctx, const void *in, uint8_t *out, unsigned long long
     const unsigned long long cap = (unsigned long long)ctx.sm_count * 32;
     if (blocks > cap) blocks = cap;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    if (sizeof(T) == 1 && vec_ok && (reinterpret_cast<uintptr_t>(out) & 1u) == 0) {
+        const unsigned long long n_chunks = n_llrs / 16;        // n is a multiple of 128
+        unsigned long long b2 = (n_chunks + kThreads - 1) / kThreads;
+        if (b2 > cap) b2 = cap;
+        llrs_to_hard_i8x16_kernel<<<(unsigned)b2, kThreads, 0, s>>>(static_cast<const uint4 *>(in),
+                                                                     reinterpret_cast<uint16_t *>(out), n_chunks);
+        count_launch();
+        return cudaGetLastError();
+    }
     llrs_to_hard_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(static_cast<const T *>(in), out, n_bytes, vec_ok);
     count_launch();
     return cudaGetLastError();
