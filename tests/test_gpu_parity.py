@@ -464,3 +464,34 @@ def test_mixed_code_batch_on_concurrent_streams(ldpc, oracle):
     torch.cuda.synchronize()
     for got, want, (code, _) in zip(results, wants, jobs):
         assert_exact([g.cpu().numpy() for g in got], want, "mixed batch %s" % code.name)
+
+
+def test_in_process_multi_device_split(oracle):
+    """labrador_ldpc_cuda_init(devices) with several GPUs: a host-pointer batch is split into contiguous
+    per-device shards (one host thread per device, no collective).  Needs >= 2 GPUs; runs in a subprocess
+    so the device list of this process stays untouched."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle"); sys.path.insert(0, %r + "/tests")
+import labrador_ldpc_b200 as L, pyoracle
+from frames import make_frames
+o = pyoracle.Oracle()
+L.init([0, 1])
+assert L.lib.labrador_ldpc_cuda_device_count() == 2
+for code, batch in ((8, 301), (0, 1001)):
+    _, cw, llrs = make_frames(o, code, batch, 2.5, seed=5, ty="i8")
+    want = o.decode_ms_batch(code, llrs, 40, nthreads=8)
+    got = L.LDPCCode(code).decode_ms_batch(llrs, 40)
+    assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want)), code
+    data = cw[:, : o.k(code) // 8].copy()
+    assert np.array_equal(L.LDPCCode(code).copy_encode_batch(data), cw)
+print("OK")
+''' % (root, root, root)
+    out = subprocess.check_output([sys.executable, "-c", script], text=True)
+    assert "OK" in out
