@@ -131,6 +131,43 @@ template <bool ON_FMA> __device__ __forceinline__ uint32_t pmin(uint32_t a, uint
 
 // Minimum over "all the other edges" for every edge of one check word: prefix/suffix minima.
 // SUF_F / PRE_F / COMB_F choose the pipe of the three groups of DC-2 minima (pipe balancing).
+// All-integer form with the three-input minimum (VIMNMX3.U16x2): prefixes P_j = min(a_0..a_{2j-1}) and suffixes
+// S_j = min(a_{2j}..) at pair boundaries only, then mu_{2j} = min3(P_j, a_{2j+1}, S_{j+1}) and
+// mu_{2j+1} = min3(P_j, a_{2j}, S_{j+1}):  2*DC - 2 instructions instead of 3*DC - 6.
+template <int DC>
+__device__ __forceinline__ void min_excluding_self3(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
+    constexpr int NPAIR = DC / 2;                  // full pairs; an odd DC leaves a[DC-1] on its own
+    constexpr bool ODD = (DC & 1) != 0;
+    uint32_t suf[kMaxDeg / 2 + 2];                 // suf[j] = min(a[2j] .. a[DC-1]), j = 1 .. NPAIR-1 (+ the odd tail)
+    if constexpr (ODD) suf[NPAIR] = a[DC - 1];
+#pragma unroll
+    for (int j = NPAIR - 1; j >= 1; j--) {
+        if (j == NPAIR - 1 && !ODD) suf[j] = __vminu2(a[2 * j], a[2 * j + 1]);
+        else suf[j] = __vimin3_u16x2(a[2 * j], a[2 * j + 1], suf[j + 1]);
+    }
+    uint32_t pre = 0;                              // pre = min(a[0] .. a[2j-1]), defined from j = 1
+#pragma unroll
+    for (int j = 0; j < NPAIR; j++) {
+        const bool has_pre = j > 0, has_suf = (j + 1 < NPAIR) || ODD;
+        if (has_pre && has_suf) {
+            mu[2 * j] = __vimin3_u16x2(pre, a[2 * j + 1], suf[j + 1]);
+            mu[2 * j + 1] = __vimin3_u16x2(pre, a[2 * j], suf[j + 1]);
+        } else if (has_suf) {
+            mu[2 * j] = __vminu2(a[2 * j + 1], suf[j + 1]);
+            mu[2 * j + 1] = __vminu2(a[2 * j], suf[j + 1]);
+        } else if (has_pre) {
+            mu[2 * j] = __vminu2(pre, a[2 * j + 1]);
+            mu[2 * j + 1] = __vminu2(pre, a[2 * j]);
+        } else {                                   // DC == 2
+            mu[2 * j] = a[2 * j + 1];
+            mu[2 * j + 1] = a[2 * j];
+        }
+        if (j + 1 < NPAIR || ODD)
+            pre = has_pre ? __vimin3_u16x2(pre, a[2 * j], a[2 * j + 1]) : __vminu2(a[2 * j], a[2 * j + 1]);
+    }
+    if constexpr (ODD) mu[DC - 1] = pre;
+}
+
 template <int DC, bool SUF_F, bool PRE_F, bool COMB_F>
 __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
     uint32_t suf[kMaxDeg];
@@ -150,12 +187,13 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 // Arithmetic variants of the kernel (kept side by side for A/B measurement):
 //   ARITH 1: integer lanes throughout (VIADDMNMX chain, two's-complement u)      -- ALU-pipe bound
 //   ARITH 3: ARITH 1 with |v| by VABSDIFF4 (no +127 offset to carry around)
+//   ARITH 5: ARITH 3 with the three-input minimum (2*DC-2 instead of 3*DC-6 minima per check word)
 //   ARITH 4: ARITH 3 with u sent in sign-magnitude (1 LOP3 + 1 IMAD on the check side) and converted to
 //            two's complement on the FMA pipe by the variable side (fp16 magic-constant add); KNOBS as ARITH 2
 //   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
 //            part of the minima on the FMA pipe (bits of KNOBS: 1 cv-min, 2 suffix, 4 prefix, 8 combine)
-template <int RATE, int M, int WPT, int ARITH, int KNOBS>
-__global__ void __launch_bounds__(M / 2 / WPT)
+template <int RATE, int M, int WPT, int ARITH, int KNOBS, int MINB = 1>
+__global__ void __launch_bounds__(M / 2 / WPT, MINB)
 decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
                        unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                        uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
@@ -403,7 +441,8 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                             sx ^= cor;                                                     // bit 7: product of signs
                         }
                     });
-                    if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
+                    if constexpr (ARITH == 5) min_excluding_self3<DC>(a, mu);
+                    else if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
                     else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
@@ -414,7 +453,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
                                 const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
                                 const uint32_t kk = __vadd2(nm, 0xff81ff81u);              // -127 or -128
                                 u = __vadd2(mu[k], kk) ^ nm;                               // +-(mu - 127), two's complement
-                            } else if constexpr (ARITH == 3) {
+                            } else if constexpr (ARITH == 3 || ARITH == 5) {
                                 const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
                                 u = __vadd2(mu[k], nm) ^ nm;                               // +-mu, two's complement
                             } else {
@@ -495,7 +534,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
     }
 }
 
-template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1>
+template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1, int MINB = 1>
 cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     typedef Proto<RATE> P;
@@ -504,7 +543,7 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
     const TmParams prm = make_params<RATE>(c);
     const size_t smem = ((size_t)NP * (M / 2) + (((size_t)P::NCOL * M / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) +
                         2 * (size_t)(P::NCOL - 1) * M;   // messages + hard bits + two LLR staging buffers
-    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS>;
+    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS, MINB>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -528,8 +567,9 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
 
 }  // namespace
 
-// Variant selection.  Three arithmetic variants are compiled per code; the default per code is the one that
-// measured fastest on B200 (profiles/r01_tm_variants.md).  LABRADOR_LDPC_TM_ARITH=1|2|3 overrides (A/B runs).
+// Variant selection.  Several arithmetic variants are compiled per code; the default per code is the one that
+// measured fastest on B200 (profiles/r01_tm_variants.md).  LABRADOR_LDPC_TM_ARITH=1|2|3|4|5 overrides (A/B runs);
+// 52 / 53 (TM5120 only) = ARITH 5 compiled for 2 / 3 resident CTAs per SM (128 / 80 registers, a few spills).
 template <int RATE, int M>
 cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const int8_t *l, uint8_t *output,
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
@@ -539,6 +579,7 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
         static const int wpt = [] { const char *e = getenv("LABRADOR_LDPC_TM_WPT"); return e ? atoi(e) : 2; }();
         if (wpt == 2) {
             if (arith == 3) return launch_tm<RATE, M, 2, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 5) return launch_tm<RATE, M, 2, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 4) return launch_tm<RATE, M, 2, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 46) return launch_tm<RATE, M, 2, 4, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 42) return launch_tm<RATE, M, 2, 4, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -547,6 +588,11 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     }
     if (arith == 1) return launch_tm<RATE, M, 1, 1, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 3) return launch_tm<RATE, M, 1, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 5) return launch_tm<RATE, M, 1, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if constexpr (RATE == 2 && M == 512) {
+        if (arith == 52) return launch_tm<RATE, M, 1, 5, 0, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+        if (arith == 53) return launch_tm<RATE, M, 1, 5, 0, 3>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    }
     if (arith == 4) return launch_tm<RATE, M, 1, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 46) return launch_tm<RATE, M, 1, 4, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     return launch_tm<RATE, M, 1, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -561,7 +607,7 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
     switch (code) {
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            *err = launch_tm_variant<1, 256>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<1, 256>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
@@ -569,15 +615,15 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            *err = launch_tm_variant<2, 512>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<2, 512>(52, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            *err = launch_tm_variant<1, 1024>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<1, 1024>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            *err = launch_tm_variant<0, 2048>(3, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            *err = launch_tm_variant<0, 2048>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;
