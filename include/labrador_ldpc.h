@@ -326,6 +326,49 @@ int labrador_ldpc_llrs_to_hard_batch_async(enum labrador_ldpc_code code, int llr
                                            const void *llrs, uint8_t *output, size_t batch,
                                            void *cuda_stream);
 
+/* ---------------------------------------------------------------------------
+ * Fused front ends of decode_ms (not in the reference).
+ *
+ * The reference's callers convert before they decode: hard_to_llrs
+ * (src/decoder.rs:484-493; capi/examples/example.c, src/lib.rs:26-49) or a
+ * float -> i8/i16 quantiser with headroom (src/decoder.rs:337-340; soft values
+ * as built in perftest/src/main.rs:13-18).  These entry points do that
+ * conversion while the decoder loads its channel LLRs, so the input crosses
+ * HBM once.  Results are bit-identical to the two-step sequence
+ *   quantise / hard_to_llrs  ->  decode_ms_{i8,i16}.
+ *
+ *   _soft_:  soft[B][n] floats;  llr = clamp(rint(soft * scale), -limit, +limit)
+ *            with round-half-to-even, a NaN product counted as 0 (an erasure);
+ *            limit in 1..127 (i8) / 1..32767 (i16), scale finite.
+ *   _hard_:  input[B][n/8] bit-packed hard decisions, MSB first;
+ *            bit 1 -> -1, bit 0 -> +1 (exactly hard_to_llrs::<i8>).
+ * Outputs, `success` and `iters_run` as for the _batch decoders above.
+ * labrador_ldpc_quantise_* is the stand-alone quantiser (same arithmetic).
+ * ------------------------------------------------------------------------- */
+#define LABRADOR_LDPC_FRONT_NONE 0
+#define LABRADOR_LDPC_FRONT_SOFT_F32 1
+#define LABRADOR_LDPC_FRONT_HARD 2
+
+int labrador_ldpc_decode_ms_i8_soft_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                          uint8_t *output, size_t batch, size_t max_iters,
+                                          uint8_t *success, uint32_t *iters_run);
+int labrador_ldpc_decode_ms_i16_soft_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                           uint8_t *output, size_t batch, size_t max_iters,
+                                           uint8_t *success, uint32_t *iters_run);
+int labrador_ldpc_decode_ms_i8_hard_batch(enum labrador_ldpc_code code, const uint8_t *input, uint8_t *output,
+                                          size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters_run);
+/* Stream-ordered form: `front` is LABRADOR_LDPC_FRONT_*, `input` holds what that front end reads. */
+int labrador_ldpc_decode_ms_front_batch_async(enum labrador_ldpc_code code, int llr_type, int front,
+                                              const void *input, float scale, int limit, uint8_t *output,
+                                              size_t batch, size_t max_iters, uint8_t *success,
+                                              uint32_t *iters_run, void *cuda_stream);
+int labrador_ldpc_quantise_i8_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                    int8_t *llrs, size_t batch);
+int labrador_ldpc_quantise_i16_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                     int16_t *llrs, size_t batch);
+int labrador_ldpc_quantise_batch_async(enum labrador_ldpc_code code, int llr_type, const float *soft, float scale,
+                                       int limit, void *llrs, size_t batch, void *cuda_stream);
+
 /* Introspection used by the tests and the benchmark harness. */
 /* Number of kernels this library has launched since load (all devices). */
 unsigned long long labrador_ldpc_kernel_launch_count(void);

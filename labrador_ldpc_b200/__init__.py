@@ -86,6 +86,15 @@ lib.labrador_ldpc_decode_bf_batch_async.argtypes = [_ci, _vp, _vp, _sz, _sz, _vp
 lib.labrador_ldpc_copy_encode_batch_async.argtypes = [_ci, _vp, _vp, _sz, _vp]
 lib.labrador_ldpc_hard_to_llrs_batch_async.argtypes = [_ci, _ci, _vp, _vp, _sz, _vp]
 lib.labrador_ldpc_llrs_to_hard_batch_async.argtypes = [_ci, _ci, _vp, _vp, _sz, _vp]
+_cf = ctypes.c_float
+lib.labrador_ldpc_decode_ms_i8_soft_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz, _sz, _vp, _vp]
+lib.labrador_ldpc_decode_ms_i16_soft_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz, _sz, _vp, _vp]
+lib.labrador_ldpc_decode_ms_i8_hard_batch.argtypes = [_ci, _vp, _vp, _sz, _sz, _vp, _vp]
+lib.labrador_ldpc_decode_ms_front_batch_async.argtypes = [_ci, _ci, _ci, _vp, _cf, _ci, _vp, _sz, _sz, _vp, _vp, _vp]
+lib.labrador_ldpc_quantise_i8_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz]
+lib.labrador_ldpc_quantise_i16_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz]
+lib.labrador_ldpc_quantise_batch_async.argtypes = [_ci, _ci, _vp, _cf, _ci, _vp, _sz, _vp]
+FRONT_NONE, FRONT_SOFT_F32, FRONT_HARD = 0, 1, 2
 
 
 def _check(rc):
@@ -310,6 +319,61 @@ class LDPCCode(enum.IntEnum):
             _check(getattr(lib, "labrador_ldpc_decode_ms_%s_batch" % ty)(
                 int(self), _ptr(llrs), _ptr(output), batch, maxiters, _ptr(success), _ptr(iters)))
         return output, success, iters
+
+    # ---- fused front ends (include/labrador_ldpc.h "Fused front ends"; csrc/front.cuh) ----
+    def _decode_front(self, front, ty, src, batch, scale, limit, maxiters, output, success, iters, stream):
+        if output is None:
+            output = _alloc_like(src, (batch, self.output_len()), np.uint8)
+        if success is None:
+            success = _alloc_like(src, (batch,), np.uint8)
+        if iters is None:
+            iters = _alloc_like(src, (batch,), np.uint32)
+        if self._batch_of(output, self.output_len()) != batch:
+            raise ValueError("output has the wrong number of frames")
+        stream = stream if stream is not None else _current_stream(src)
+        if stream is not None:
+            _check(lib.labrador_ldpc_decode_ms_front_batch_async(
+                int(self), LLR_TYPES[ty], front, _ptr(src), scale, limit, _ptr(output), batch, maxiters,
+                _ptr(success), _ptr(iters), stream))
+        elif front == FRONT_HARD:
+            _check(lib.labrador_ldpc_decode_ms_i8_hard_batch(int(self), _ptr(src), _ptr(output), batch, maxiters,
+                                                             _ptr(success), _ptr(iters)))
+        else:
+            _check(getattr(lib, "labrador_ldpc_decode_ms_%s_soft_batch" % ty)(
+                int(self), _ptr(src), scale, limit, _ptr(output), batch, maxiters, _ptr(success), _ptr(iters)))
+        return output, success, iters
+
+    def decode_ms_soft_batch(self, soft, scale, limit, maxiters, ty="i8", output=None, success=None, iters=None,
+                             stream=None):
+        """decode_ms::<ty> of clamp(rint(soft * scale), -limit, limit), quantised inside the decoder (f32 soft values)."""
+        if ty not in ("i8", "i16"):
+            raise ValueError("soft front end quantises to i8 or i16")
+        if _llr_type(soft) != "f32":
+            raise ValueError("soft values must be float32")
+        batch = self._batch_of(soft, self.n() * 4)
+        return self._decode_front(FRONT_SOFT_F32, ty, soft, batch, float(scale), int(limit), maxiters, output, success,
+                                  iters, stream)
+
+    def decode_ms_hard_batch(self, input, maxiters, output=None, success=None, iters=None, stream=None):
+        """decode_ms::<i8> of hard_to_llrs(input), converted inside the decoder (bit-packed hard decisions)."""
+        batch = self._batch_of(input, self.n() // 8)
+        return self._decode_front(FRONT_HARD, "i8", input, batch, 1.0, 0, maxiters, output, success, iters, stream)
+
+    def quantise_batch(self, soft, scale, limit, ty="i8", llrs=None, stream=None):
+        """llrs = clamp(rint(soft * scale), -limit, limit) as i8 / i16 (the stand-alone form of the soft front end)."""
+        if ty not in ("i8", "i16"):
+            raise ValueError("quantise produces i8 or i16")
+        batch = self._batch_of(soft, self.n() * 4)
+        if llrs is None:
+            llrs = _alloc_like(soft, (batch, self.n()), _NP_OF[ty])
+        stream = stream if stream is not None else _current_stream(soft)
+        if stream is not None:
+            _check(lib.labrador_ldpc_quantise_batch_async(int(self), LLR_TYPES[ty], _ptr(soft), float(scale), int(limit),
+                                                          _ptr(llrs), batch, stream))
+        else:
+            _check(getattr(lib, "labrador_ldpc_quantise_%s_batch" % ty)(int(self), _ptr(soft), float(scale), int(limit),
+                                                                        _ptr(llrs), batch))
+        return llrs
 
     def decode_bf_batch(self, input, maxiters, output=None, success=None, iters=None, stream=None):
         batch = self._batch_of(input, self.n() // 8)

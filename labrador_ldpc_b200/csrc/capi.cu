@@ -27,11 +27,21 @@ int common_kind(std::initializer_list<const void *> ptrs, int *device) {
     return kind == -2 ? 0 : kind;
 }
 
+// front: what `llrs` holds (runtime.h) -- LLRs of type ty, float soft values quantised to ty on load, or hard bits.
 int decode_ms_impl(int code, int ty, const void *llrs, uint8_t *output, size_t batch, size_t max_iters,
-                   uint8_t *success, uint32_t *iters, bool async, cudaStream_t stream) {
+                   uint8_t *success, uint32_t *iters, bool async, cudaStream_t stream, const Front &front = Front()) {
     const CodeInfo *c = info(code);
     if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
     if (ty < 0 || ty >= kNumLlrTypes) return fail(LDPC_ERR_BAD_ARGUMENT, "bad llr_type");
+    if (!front_supported(front.kind, ty))
+        return fail(LDPC_ERR_BAD_ARGUMENT, "front end not available for this llr_type (soft: i8/i16, hard: i8)");
+    if (front.kind == kFrontSoftF32) {
+        const float max_limit = ty == kI8 ? 127.0f : 32767.0f;
+        if (!(front.limit >= 1.0f && front.limit <= max_limit) || front.limit != (float)(int)front.limit)
+            return fail(LDPC_ERR_BAD_ARGUMENT, "limit must be an integer in 1..127 (i8) or 1..32767 (i16)");
+        if (!(front.scale == front.scale) || front.scale - front.scale != 0.0f)
+            return fail(LDPC_ERR_BAD_ARGUMENT, "scale must be finite");
+    }
     if (batch == 0) return LDPC_OK;
     if (!llrs || !output) return fail(LDPC_ERR_NULL_POINTER, "llrs/output must not be NULL");
     int dev = -1;
@@ -40,11 +50,11 @@ int decode_ms_impl(int code, int ty, const void *llrs, uint8_t *output, size_t b
     if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
     if (kind == 1) {
         return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
-            return launch_decode_ms(ctx, code, ty, llrs, output, batch, max_iters, success, iters, st);
+            return launch_decode_ms(ctx, code, ty, llrs, output, batch, max_iters, success, iters, st, front);
         });
     }
     std::vector<HostArray> arrays;
-    arrays.push_back({llrs, nullptr, (size_t)c->n * llr_size(ty)});
+    arrays.push_back({llrs, nullptr, front_frame_bytes(front, c->n, ty)});
     arrays.push_back({nullptr, output, c->output_len()});
     const int si = success ? (int)arrays.size() : -1;
     if (success) arrays.push_back({nullptr, success, 1});
@@ -53,8 +63,44 @@ int decode_ms_impl(int code, int ty, const void *llrs, uint8_t *output, size_t b
     return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
         return launch_decode_ms(ctx, code, ty, d[0], static_cast<uint8_t *>(d[1]), nf, max_iters,
                                 si >= 0 ? static_cast<uint8_t *>(d[si]) : nullptr,
-                                ii >= 0 ? static_cast<uint32_t *>(d[ii]) : nullptr, st);
+                                ii >= 0 ? static_cast<uint32_t *>(d[ii]) : nullptr, st, front);
     });
+}
+
+int quantise_impl(int code, int ty, const float *soft, float scale, int limit, void *llrs, size_t batch, bool async,
+                  cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (ty != kI8 && ty != kI16) return fail(LDPC_ERR_BAD_ARGUMENT, "quantise produces i8 or i16 LLRs");
+    if (limit < 1 || limit > (ty == kI8 ? 127 : 32767))
+        return fail(LDPC_ERR_BAD_ARGUMENT, "limit must be in 1..127 (i8) or 1..32767 (i16)");
+    if (!(scale == scale) || scale - scale != 0.0f) return fail(LDPC_ERR_BAD_ARGUMENT, "scale must be finite");
+    if (batch == 0) return LDPC_OK;
+    if (!soft || !llrs) return fail(LDPC_ERR_NULL_POINTER, "soft/llrs must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({soft, llrs}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    const float flimit = (float)limit;
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_quantise(ctx, code, ty, soft, llrs, batch, scale, flimit, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({soft, nullptr, (size_t)c->n * 4});
+    arrays.push_back({nullptr, llrs, (size_t)c->n * llr_size(ty)});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_quantise(ctx, code, ty, static_cast<const float *>(d[0]), d[1], nf, scale, flimit, st);
+    });
+}
+
+Front soft_front(float scale, int limit) {
+    Front f;
+    f.kind = kFrontSoftF32;
+    f.scale = scale;
+    f.limit = (float)limit;
+    return f;
 }
 
 int decode_bf_impl(int code, const uint8_t *input, uint8_t *output, size_t batch, size_t max_iters,
@@ -295,6 +341,54 @@ int labrador_ldpc_hard_to_llrs_batch_async(enum labrador_ldpc_code code, int llr
 int labrador_ldpc_llrs_to_hard_batch_async(enum labrador_ldpc_code code, int llr_type, const void *llrs,
                                            uint8_t *output, size_t batch, void *cuda_stream) {
     return l2h_impl(code, llr_type, llrs, output, batch, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+// ---- fused front ends (csrc/front.cuh) ----
+int labrador_ldpc_decode_ms_i8_soft_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                          uint8_t *output, size_t batch, size_t max_iters, uint8_t *success,
+                                          uint32_t *iters_run) {
+    return decode_ms_impl(code, kI8, soft, output, batch, max_iters, success, iters_run, false, nullptr,
+                          soft_front(scale, limit));
+}
+
+int labrador_ldpc_decode_ms_i16_soft_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                           uint8_t *output, size_t batch, size_t max_iters, uint8_t *success,
+                                           uint32_t *iters_run) {
+    return decode_ms_impl(code, kI16, soft, output, batch, max_iters, success, iters_run, false, nullptr,
+                          soft_front(scale, limit));
+}
+
+int labrador_ldpc_decode_ms_i8_hard_batch(enum labrador_ldpc_code code, const uint8_t *input, uint8_t *output,
+                                          size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters_run) {
+    Front f;
+    f.kind = kFrontHard;
+    return decode_ms_impl(code, kI8, input, output, batch, max_iters, success, iters_run, false, nullptr, f);
+}
+
+int labrador_ldpc_decode_ms_front_batch_async(enum labrador_ldpc_code code, int llr_type, int front, const void *input,
+                                              float scale, int limit, uint8_t *output, size_t batch, size_t max_iters,
+                                              uint8_t *success, uint32_t *iters_run, void *cuda_stream) {
+    Front f;
+    if (front == LABRADOR_LDPC_FRONT_SOFT_F32) f = soft_front(scale, limit);
+    else if (front == LABRADOR_LDPC_FRONT_HARD) f.kind = kFrontHard;
+    else if (front != LABRADOR_LDPC_FRONT_NONE) return fail(LDPC_ERR_BAD_ARGUMENT, "bad front");
+    return decode_ms_impl(code, llr_type, input, output, batch, max_iters, success, iters_run, true,
+                          static_cast<cudaStream_t>(cuda_stream), f);
+}
+
+int labrador_ldpc_quantise_i8_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                    int8_t *llrs, size_t batch) {
+    return quantise_impl(code, kI8, soft, scale, limit, llrs, batch, false, nullptr);
+}
+
+int labrador_ldpc_quantise_i16_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
+                                     int16_t *llrs, size_t batch) {
+    return quantise_impl(code, kI16, soft, scale, limit, llrs, batch, false, nullptr);
+}
+
+int labrador_ldpc_quantise_batch_async(enum labrador_ldpc_code code, int llr_type, const float *soft, float scale,
+                                       int limit, void *llrs, size_t batch, void *cuda_stream) {
+    return quantise_impl(code, llr_type, soft, scale, limit, llrs, batch, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
 unsigned long long labrador_ldpc_kernel_launch_count(void) { return launch_count(); }

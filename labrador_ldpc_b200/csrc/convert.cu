@@ -5,6 +5,7 @@
 // MSB first within each byte; the inverse uses hard_bit (`< 0`).
 #include <cuda_runtime.h>
 
+#include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
 
@@ -118,7 +119,55 @@ cudaError_t l2h(DeviceCtx &ctx, const void *in, uint8_t *out, unsigned long long
     return cudaGetLastError();
 }
 
+// Stand-alone quantiser (the un-fused form of front.cuh's kFrontSoftF32): 16 soft values (four 16-byte
+// loads) -> 16 LLRs per thread and iteration; scalar tail and unaligned buffers element-wise.
+template <class T>
+__global__ void quantise_kernel(const float *__restrict__ soft, T *__restrict__ out, unsigned long long count,
+                                const float scale, const float limit, const bool vec_ok) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long n16 = vec_ok ? count / 16 : 0;
+    for (unsigned long long j = tid; j < n16; j += stride) {
+        __align__(16) T q[16];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const float4 f = reinterpret_cast<const float4 *>(soft)[j * 4 + v];
+            q[4 * v + 0] = (T)quantise_soft(f.x, scale, limit);
+            q[4 * v + 1] = (T)quantise_soft(f.y, scale, limit);
+            q[4 * v + 2] = (T)quantise_soft(f.z, scale, limit);
+            q[4 * v + 3] = (T)quantise_soft(f.w, scale, limit);
+        }
+#pragma unroll
+        for (int v = 0; v < (int)sizeof(q) / 16; v++)
+            reinterpret_cast<uint4 *>(out)[j * (sizeof(q) / 16) + v] = reinterpret_cast<const uint4 *>(q)[v];
+    }
+    for (unsigned long long i = n16 * 16 + tid; i < count; i += stride) out[i] = (T)quantise_soft(soft[i], scale, limit);
+}
+
+template <class T>
+cudaError_t quantise(DeviceCtx &ctx, const float *soft, void *out, unsigned long long count, float scale, float limit,
+                     cudaStream_t s) {
+    if (count == 0) return cudaSuccess;
+    unsigned long long blocks = (count / 16 + kThreads - 1) / kThreads + 1;
+    const unsigned long long cap = (unsigned long long)ctx.sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(soft) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    quantise_kernel<T><<<(unsigned)blocks, kThreads, 0, s>>>(soft, static_cast<T *>(out), count, scale, limit, vec_ok);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace
+
+cudaError_t launch_quantise(DeviceCtx &ctx, int code, int llr_type, const float *soft, void *llrs, size_t batch,
+                            float scale, float limit, cudaStream_t stream) {
+    const unsigned long long count = (unsigned long long)batch * ctx.codes[code].n;
+    switch (llr_type) {
+        case kI8: return quantise<int8_t>(ctx, soft, llrs, count, scale, limit, stream);
+        case kI16: return quantise<int16_t>(ctx, soft, llrs, count, scale, limit, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 cudaError_t launch_hard_to_llrs(DeviceCtx &ctx, int code, int llr_type, const uint8_t *input, void *llrs,
                                 size_t batch, cudaStream_t stream) {

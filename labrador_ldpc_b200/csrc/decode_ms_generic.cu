@@ -18,6 +18,7 @@
 // slot owned by the CTA.
 #include <cuda_runtime.h>
 
+#include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
 
@@ -33,12 +34,13 @@ struct MsLayout {
     bool v_in_smem, llr_in_smem;
 };
 
-template <class T>
+template <class T, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(kThreads)
-decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay, const T *__restrict__ llrs_all,
+decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay,
+                         const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
                          uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
                          uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
-                         T *__restrict__ vscratch) {
+                         T *__restrict__ vscratch, const float fscale, const float flimit) {
     typedef Arith<T> A;
     extern __shared__ __align__(16) unsigned char smem[];
     T *v = lay.v_in_smem ? reinterpret_cast<T *>(smem + lay.v_off)
@@ -55,14 +57,14 @@ decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay, const T *__r
     const int out_len = nv / 8;
 
     for (unsigned long long frame = blockIdx.x; frame < batch; frame += gridDim.x) {
-        const T *llr_g = llrs_all + frame * (unsigned long long)n;
+        const typename FrontSrc<FRONT, T>::type *llr_g =
+            llrs_all + frame * (unsigned long long)(FRONT == kFrontHard ? n / 8 : n);   // front.cuh
         // Zero-initialised state, every call (reference :368, :374).
         for (int i = tid; i < ne; i += kThreads) v[i] = A::zero();
         for (int i = tid; i < nc; i += kThreads) { min1[i] = A::zero(); min2[i] = A::zero(); sgn[i] = 0; }
         for (int i = tid; i < nv; i += kThreads) hb[i] = 0;
         if (lay.llr_in_smem)
-            for (int i = tid; i < n; i += kThreads) llr_s[i] = llr_g[i];
-        const T *llr = lay.llr_in_smem ? llr_s : llr_g;
+            for (int i = tid; i < n; i += kThreads) llr_s[i] = (T)front_load<FRONT, T>(llr_g, i, fscale, flimit);
         __syncthreads();
 
         unsigned iters_run = max_iters;
@@ -70,7 +72,8 @@ decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay, const T *__r
         for (unsigned iter = 0; iter < max_iters; iter++) {
             // ---- phase A: variables ----
             for (int a = tid; a < nv; a += kThreads) {
-                T va = a < n ? llr[a] : A::zero();                          // :382-383
+                T va = A::zero();                                           // :382-383
+                if (a < n) va = lay.llr_in_smem ? llr_s[a] : (T)front_load<FRONT, T>(llr_g, a, fscale, flimit);
                 T ul[kMaxVarDeg];
                 T vold[kMaxVarDeg];
 #pragma unroll
@@ -166,12 +169,13 @@ MsLayout make_layout(const DeviceCode &c, int max_smem) {
     return l;
 }
 
-template <class T>
+template <class T, int FRONT = kFrontNone>
 cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
-                           size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+                           size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                           const Front &front = Front()) {
     const DeviceCode &dc = ctx.codes[code];
     const MsLayout lay = make_layout<T>(dc, ctx.max_smem_optin);
-    auto kern = decode_ms_generic_kernel<T>;
+    auto kern = decode_ms_generic_kernel<T, FRONT>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total);
     if (err != cudaSuccess) return err;
     unsigned long long grid = batch;
@@ -192,8 +196,9 @@ cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *
     }
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    kern<<<(unsigned)grid, kThreads, lay.total, stream>>>(dc, lay, static_cast<const T *>(llrs), output,
-                                                          (unsigned long long)batch, mi, success, iters, scratch);
+    kern<<<(unsigned)grid, kThreads, lay.total, stream>>>(dc, lay, static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs),
+                                                          output, (unsigned long long)batch, mi, success, iters, scratch,
+                                                          front.scale, front.limit);
     count_launch();
     return cudaGetLastError();
 }
@@ -202,7 +207,14 @@ cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *
 
 cudaError_t launch_decode_ms_generic(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
                                      size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const Front &front) {
+    if (front.kind == kFrontSoftF32 && llr_type == kI8)
+        return launch_generic<int8_t, kFrontSoftF32>(ctx, code, llrs, output, batch, max_iters, success, iters, stream, front);
+    if (front.kind == kFrontSoftF32 && llr_type == kI16)
+        return launch_generic<int16_t, kFrontSoftF32>(ctx, code, llrs, output, batch, max_iters, success, iters, stream, front);
+    if (front.kind == kFrontHard && llr_type == kI8)
+        return launch_generic<int8_t, kFrontHard>(ctx, code, llrs, output, batch, max_iters, success, iters, stream, front);
+    if (front.kind != kFrontNone) return cudaErrorInvalidValue;
     switch (llr_type) {
         case kI8: return launch_generic<int8_t>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);
         case kI16: return launch_generic<int16_t>(ctx, code, llrs, output, batch, max_iters, success, iters, stream);

@@ -18,6 +18,7 @@
 
 #include <type_traits>
 
+#include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
 
@@ -53,11 +54,13 @@ struct TcParams { uint8_t shift[32]; };
 
 constexpr int kWarpsPerCta = 4;
 
-template <int M, class T>
+template <int M, class T, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
-decode_ms_tc_kernel(const TcParams prm, const T *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
+decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
+                    uint8_t *__restrict__ out_all,
                     unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
-                    uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+                    uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
+                    const float fscale, const float flimit) {
     typedef Arith<T> A;
     typedef typename MsgStore<T>::type ST;          // shared-memory storage type of a message
     typedef typename A::C CT;                       // register (compute) type
@@ -84,14 +87,15 @@ decode_ms_tc_kernel(const TcParams prm, const T *__restrict__ llrs_all, uint8_t 
         if (base >= batch) break;
         const unsigned long long frame = base + cwl;
         const bool live = frame < batch;                 // the second codeword of a TC128 warp may not exist
-        const T *llr = llrs_all + (live ? frame : base) * (unsigned long long)N;
+        const typename FrontSrc<FRONT, T>::type *llr =
+            llrs_all + (live ? frame : base) * (unsigned long long)(FRONT == kFrontHard ? N / 8 : N);   // front.cuh
 
         CT Lv[8][EPT], vold[32][EPT];
 #pragma unroll
         for (int ei = 0; ei < EPT; ei++) {
             const int e = sl + ei * G;
 #pragma unroll
-            for (int c = 0; c < 8; c++) Lv[c][ei] = (CT)llr[c * M + e];
+            for (int c = 0; c < 8; c++) Lv[c][ei] = front_load<FRONT, T>(llr, c * M + e, fscale, flimit);
 #pragma unroll
             for (int b = 0; b < 32; b++) { vold[b][ei] = A::zero(); msg[b * M + e] = (ST)A::zero(); }
 #pragma unroll
@@ -203,15 +207,16 @@ decode_ms_tc_kernel(const TcParams prm, const T *__restrict__ llrs_all, uint8_t 
     }
 }
 
-template <int M, class T>
+template <int M, class T, int FRONT = kFrontNone>
 cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
-                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                      const Front &front = Front()) {
     constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
     TcParams prm{};
     for (int b = 0; b < 32; b++) prm.shift[b] = (uint8_t)c.blocks[b].shift;
     const size_t warp_bytes = ((sizeof(typename MsgStore<T>::type) * CWW * 32 * M + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kWarpsPerCta;
-    auto kern = decode_ms_tc_kernel<M, T>;
+    auto kern = decode_ms_tc_kernel<M, T, FRONT>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -230,8 +235,9 @@ cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     e = tm::next_counter(ctx.device, stream, &counter);
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    kern<<<(unsigned)grid, 32 * kWarpsPerCta, smem, stream>>>(prm, static_cast<const T *>(llrs), output,
-                                                               (unsigned long long)batch, mi, success, iters, counter);
+    kern<<<(unsigned)grid, 32 * kWarpsPerCta, smem, stream>>>(
+        prm, static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs), output, (unsigned long long)batch, mi, success,
+        iters, counter, front.scale, front.limit);
     count_launch();
     return cudaGetLastError();
 }
@@ -248,7 +254,19 @@ bool tc_structure_matches(const CodeInfo &c) {
 
 template <int M>
 bool tc_dispatch(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *llrs, uint8_t *output, size_t batch,
-                 size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err) {
+                 size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err,
+                 const Front &front) {
+    if (front.kind != kFrontNone) {      // fused front ends: (soft, i8 | i16) and (hard, i8)
+        if (front.kind == kFrontSoftF32 && llr_type == kI8)
+            *err = launch_tc<M, int8_t, kFrontSoftF32>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+        else if (front.kind == kFrontSoftF32 && llr_type == kI16)
+            *err = launch_tc<M, int16_t, kFrontSoftF32>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+        else if (front.kind == kFrontHard && llr_type == kI8)
+            *err = launch_tc<M, int8_t, kFrontHard>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+        else
+            return false;
+        return true;
+    }
     switch (llr_type) {
         case kI8: *err = launch_tc<M, int8_t>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
         case kI16: *err = launch_tc<M, int16_t>(ctx, c, llrs, output, batch, max_iters, success, iters, stream); return true;
@@ -262,14 +280,15 @@ bool tc_dispatch(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *ll
 }  // namespace
 
 bool launch_decode_ms_tc(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
-                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err) {
+                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err,
+                         const Front &front) {
     if (code < 0 || code > 2) return false;
     const CodeInfo &c = *code_info(code);
     if (!tc_structure_matches(c)) return false;
     switch (c.m) {
-        case 16: return tc_dispatch<16>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
-        case 32: return tc_dispatch<32>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
-        case 64: return tc_dispatch<64>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+        case 16: return tc_dispatch<16>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
+        case 32: return tc_dispatch<32>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
+        case 64: return tc_dispatch<64>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         default: return false;
     }
 }

@@ -44,6 +44,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "front.cuh"
 #include "runtime.h"
 #include "tm_common.cuh"
 
@@ -192,12 +193,17 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 //            two's complement on the FMA pipe by the variable side (fp16 magic-constant add); KNOBS as ARITH 2
 //   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
 //            part of the minima on the FMA pipe (bits of KNOBS: 1 cv-min, 2 suffix, 4 prefix, 8 combine)
-template <int RATE, int M, int WPT, int ARITH, int KNOBS, int MINB = 1>
+// FRONT (front.cuh): what a frame of `llrs_all` holds -- n int8 LLRs, n float soft values quantised on load,
+// or n/8 bytes of hard decisions; the frame is staged in shared memory by the same bulk copy in every case.
+template <int RATE, int M, int WPT, int ARITH, int KNOBS, int MINB = 1, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(M / 2 / WPT, MINB)
-decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
+decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
+                       uint8_t *__restrict__ out_all,
                        unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                        uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
-                       const uint32_t one /* == 1: keeps the borrow-free subtractions on the FMA pipe (IMAD) */) {
+                       const uint32_t one /* == 1: keeps the borrow-free subtractions on the FMA pipe (IMAD) */,
+                       const float fscale, const float flimit) {
+    typedef typename FrontSrc<FRONT, int8_t>::type Src;
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
     constexpr int NP = count_p<P>(NB), NI = NB - NP;
@@ -220,7 +226,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t *msg = smem_u32;                       // [NP][M/2] permutation-block messages, check order
     uint32_t *hb = msg + NP * (M / 2);              // [HBW] packed hard decisions, bit i of word j = variable 32j+i
-    int8_t *stage = reinterpret_cast<int8_t *>(hb + ((HBW + 3) & ~3));   // [2][N] LLR staging (bulk-copy destination)
+    constexpr unsigned FB = FRONT == kFrontSoftF32 ? N * 4 : FRONT == kFrontHard ? N / 8 : N;   // input bytes per frame
+    static_assert(FB % 16 == 0, "bulk copies move multiples of 16 bytes");
+    unsigned char *stage = reinterpret_cast<unsigned char *>(hb + ((HBW + 3) & ~3));   // [2][FB] input staging (bulk-copy destination)
+    const unsigned char *in_all = reinterpret_cast<const unsigned char *>(llrs_all);
     __shared__ unsigned long long s_frame[2];
     __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -266,7 +275,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const unsigned long long f0 = atomicAdd(counter, 1ull);
         s_frame[0] = f0;
-        if (use_bulk && f0 < batch) bulk_load(stage, llrs_all + f0 * (unsigned long long)N, N, &s_bar[0]);
+        if (use_bulk && f0 < batch) bulk_load(stage, in_all + f0 * (unsigned long long)FB, FB, &s_bar[0]);
     }
     __syncthreads();
     unsigned cur = 0, bar_parity = 0;    // bit b of bar_parity = phase parity of s_bar[b]
@@ -278,15 +287,15 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
             const unsigned long long fn = atomicAdd(counter, 1ull);
             s_frame[cur ^ 1] = fn;
             if (use_bulk && fn < batch)
-                bulk_load(stage + (cur ^ 1) * N, llrs_all + fn * (unsigned long long)N, N, &s_bar[cur ^ 1]);
+                bulk_load(stage + (cur ^ 1) * FB, in_all + fn * (unsigned long long)FB, FB, &s_bar[cur ^ 1]);
         }
-        const int8_t *llr;
+        const Src *llr;
         if (use_bulk) {
             mbar_wait(&s_bar[cur], (bar_parity >> cur) & 1u);
             bar_parity ^= 1u << cur;
-            llr = stage + cur * N;
+            llr = reinterpret_cast<const Src *>(stage + cur * FB);
         } else {
-            llr = llrs_all + frame * (unsigned long long)N;
+            llr = reinterpret_cast<const Src *>(in_all + frame * (unsigned long long)FB);
         }
 
         // ---- per-frame state: everything zero, every call (:368, :374) ----
@@ -300,7 +309,8 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
 #pragma unroll
             for (int c = 0; c < NCOL; c++) {
                 if (c < NCOL - 1) {
-                    const int l0 = llr[c * M + e0], l1 = llr[c * M + e0 + S];
+                    const int l0 = front_load<FRONT, int8_t>(llr, c * M + e0, fscale, flimit);
+                    const int l1 = front_load<FRONT, int8_t>(llr, c * M + e0 + S, fscale, flimit);
                     Lb[c][wi] = (uint32_t)(l0 + 128) | ((uint32_t)(l1 + 128) << 16);
                 } else {
                     Lb[c][wi] = 0x00800080u;                                      // :383
@@ -534,16 +544,17 @@ decode_ms_tm_i8_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, 
     }
 }
 
-template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1, int MINB = 1>
-cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uint8_t *output, size_t batch,
-                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1, int MINB = 1, int FRONT = kFrontNone>
+cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                      const Front &front = Front()) {
     typedef Proto<RATE> P;
     constexpr int NP = count_p<P>(P::NB);
     constexpr int NT = M / 2 / WPT;
     const TmParams prm = make_params<RATE>(c);
     const size_t smem = ((size_t)NP * (M / 2) + (((size_t)P::NCOL * M / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) +
-                        2 * (size_t)(P::NCOL - 1) * M;   // messages + hard bits + two LLR staging buffers
-    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS, MINB>;
+                        2 * front_frame_bytes(front, (P::NCOL - 1) * M, kI8);   // messages + hard bits + two input staging buffers
+    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS, MINB, FRONT>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -560,7 +571,9 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
     e = next_counter(ctx.device, stream, &counter);
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, llrs, output, (unsigned long long)batch, mi, success, iters, counter, 1u);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, static_cast<const typename FrontSrc<FRONT, int8_t>::type *>(llrs), output,
+                                               (unsigned long long)batch, mi, success, iters, counter, 1u, front.scale,
+                                               front.limit);
     count_launch();
     return cudaGetLastError();
 }
@@ -571,7 +584,7 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const int8_t *llrs, uin
 // measured fastest on B200 (profiles/r01_tm_variants.md).  LABRADOR_LDPC_TM_ARITH=1|2|3|4|5 overrides (A/B runs);
 // 52 / 53 (TM5120 only) = ARITH 5 compiled for 2 / 3 resident CTAs per SM (128 / 80 registers, a few spills).
 template <int RATE, int M>
-cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const int8_t *l, uint8_t *output,
+cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const void *l, uint8_t *output,
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 0; }();
     const int arith = forced ? forced : default_arith;
@@ -598,32 +611,51 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     return launch_tm<RATE, M, 1, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
 }
 
+// The fused front ends (front.cuh) are compiled for each code's default variant only.
+template <int RATE, int M, int WPT, int ARITH, int KNOBS, int MINB>
+cudaError_t launch_tm_front(const Front &front, DeviceCtx &ctx, const CodeInfo &c, const void *l, uint8_t *output,
+                            size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    if (front.kind == kFrontSoftF32)
+        return launch_tm<RATE, M, WPT, ARITH, KNOBS, MINB, kFrontSoftF32>(ctx, c, l, output, batch, max_iters, success,
+                                                                           iters, stream, front);
+    if (front.kind == kFrontHard)
+        return launch_tm<RATE, M, WPT, ARITH, KNOBS, MINB, kFrontHard>(ctx, c, l, output, batch, max_iters, success, iters,
+                                                                        stream, front);
+    return cudaErrorInvalidValue;
+}
+
 // Returns true (and launches) if a specialised kernel exists for (code, i8).
 bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
-                            cudaError_t *err) {
+                            cudaError_t *err, const Front &front) {
     const CodeInfo &c = *code_info(code);
-    const int8_t *l = static_cast<const int8_t *>(llrs);
+    const void *l = llrs;
+    const bool ff = front.kind != kFrontNone;
     switch (code) {
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            *err = launch_tm_variant<1, 256>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 256, 1, 5, 0, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 256>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
-            *err = launch_tm_variant<0, 512>(2, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 512, 1, 2, 6, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 512>(2, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            *err = launch_tm_variant<2, 512>(52, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 512, 1, 5, 0, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<2, 512>(52, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            *err = launch_tm_variant<1, 1024>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 1024, 1, 5, 0, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 1024>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            *err = launch_tm_variant<0, 2048>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 2048, 2, 5, 0, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 2048>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;

@@ -14,6 +14,7 @@
 
 #include <cstdlib>
 
+#include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
 #include "tm_common.cuh"
@@ -25,11 +26,13 @@ namespace {
 
 constexpr int kMaxDegW = 18;
 
-template <int RATE, int M, class T, int NT>
+template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(NT)
-decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
+decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
+                         uint8_t *__restrict__ out_all,
                          unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
-                         uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+                         uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
+                         const float fscale, const float flimit) {
     typedef Proto<RATE> P;
     typedef Arith<T> A;
     typedef typename MsgStore<T>::type ST;          // shared-memory storage type of a message
@@ -72,7 +75,8 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
         __syncthreads();
         const unsigned long long frame = s_frame;
         if (frame >= batch) break;
-        const T *llr = llrs_all + frame * (unsigned long long)N;
+        const typename FrontSrc<FRONT, T>::type *llr =
+            llrs_all + frame * (unsigned long long)(FRONT == kFrontHard ? N / 8 : N);   // front.cuh
 
         // zero-initialised state, every call (:368, :374)
         CT Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[NB][EPT];
@@ -80,7 +84,7 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
         for (int ei = 0; ei < EPT; ei++) {
             const int e = tid + ei * NT;
 #pragma unroll
-            for (int c = 0; c < NCOL; c++) Lv[c][ei] = c < NCOL - 1 ? (CT)llr[c * M + e] : A::zero();   // :382-383
+            for (int c = 0; c < NCOL; c++) Lv[c][ei] = c < NCOL - 1 ? front_load<FRONT, T>(llr, c * M + e, fscale, flimit) : A::zero();   // :382-383
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][ei] = A::zero();
 #pragma unroll
@@ -260,14 +264,15 @@ decode_ms_tm_wide_kernel(const TmParams prm, const T *__restrict__ llrs_all, uin
     }
 }
 
-template <int RATE, int M, class T, int NT>
+template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
 cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
-                        size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+                        size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
+                        const Front &front = Front()) {
     typedef Proto<RATE> P;
     constexpr int NP = count_p<P>(P::NB);
     const TmParams prm = make_params<RATE>(c);
     const size_t smem = sizeof(typename MsgStore<T>::type) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32;
-    auto kern = decode_ms_tm_wide_kernel<RATE, M, T, NT>;
+    auto kern = decode_ms_tm_wide_kernel<RATE, M, T, NT, FRONT>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -284,8 +289,9 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
     e = next_counter(ctx.device, stream, &counter);
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, static_cast<const T *>(llrs), output, (unsigned long long)batch,
-                                                mi, success, iters, counter);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(prm, static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs), output,
+                                               (unsigned long long)batch, mi, success, iters, counter, front.scale,
+                                               front.limit);
     count_launch();
     return cudaGetLastError();
 }
@@ -293,7 +299,24 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
 template <int RATE, int M, int NT, bool WITH_I8>
 bool dispatch_type(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *llrs, uint8_t *output,
                    size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
-                   cudaError_t *err) {
+                   cudaError_t *err, const Front &front) {
+    if (front.kind != kFrontNone) {      // fused front ends: (soft, i8 | i16) and (hard, i8)
+        if (front.kind == kFrontSoftF32 && llr_type == kI16) {
+            *err = launch_wide<RATE, M, int16_t, NT, kFrontSoftF32>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+            return true;
+        }
+        if constexpr (WITH_I8) {
+            if (front.kind == kFrontSoftF32 && llr_type == kI8) {
+                *err = launch_wide<RATE, M, int8_t, NT, kFrontSoftF32>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+                return true;
+            }
+            if (front.kind == kFrontHard && llr_type == kI8) {
+                *err = launch_wide<RATE, M, int8_t, NT, kFrontHard>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+                return true;
+            }
+        }
+        return false;
+    }
     switch (llr_type) {
         case kI8:
             if constexpr (WITH_I8) {
@@ -324,27 +347,27 @@ bool dispatch_type(DeviceCtx &ctx, const CodeInfo &c, int llr_type, const void *
 // Returns true (and launches) if the wide-lane TM kernel covers (code, llr_type).
 bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
                               size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
-                              cudaError_t *err) {
+                              cudaError_t *err, const Front &front) {
     const CodeInfo &c = *code_info(code);
     switch (code) {
         case 3:   // TM1280: every type (M = 128 is too small for the packed i8 kernel)
             if (!structure_matches<2>(c) || c.m != 128) return false;
-            return dispatch_type<2, 128, 128, true>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+            return dispatch_type<2, 128, 128, true>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            return dispatch_type<1, 256, 256, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+            return dispatch_type<1, 256, 256, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
-            return dispatch_type<0, 512, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+            return dispatch_type<0, 512, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            return dispatch_type<2, 512, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+            return dispatch_type<2, 512, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            return dispatch_type<1, 1024, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+            return dispatch_type<1, 1024, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            return dispatch_type<0, 2048, 1024, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err);
+            return dispatch_type<0, 2048, 1024, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         default:
             return false;
     }

@@ -19,18 +19,19 @@ namespace ldpc {
 // implemented in decode_ms_generic.cu / decode_ms_tm.cu
 cudaError_t launch_decode_ms_generic(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
                                      size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, const Front &front);
 
 bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
-                            cudaError_t *err);
+                            cudaError_t *err, const Front &front);
 bool has_decode_ms_tm_i8(int code);
 bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
                               size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
-                              cudaError_t *err);
+                              cudaError_t *err, const Front &front);
 bool has_decode_ms_tm_wide(int code, int llr_type);
 bool launch_decode_ms_tc(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
-                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err);
+                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err,
+                         const Front &front);
 bool has_decode_ms_tc(int code);
 
 namespace {
@@ -241,20 +242,30 @@ int classify_pointer(const void *p, int *device) {
 // ---------------------------------------------------------------------------
 cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
                              size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const Front &front) {
     if (batch == 0) return cudaSuccess;
+    if (front.kind != kFrontNone && !front_supported(front.kind, llr_type)) return cudaErrorInvalidValue;
     if (llr_type == kI8 && !force_generic()) {
         cudaError_t err = cudaSuccess;
-        if (launch_decode_ms_tm_i8(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err)) return err;
+        if (launch_decode_ms_tm_i8(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err, front))
+            return err;
     }
     if (!force_generic()) {
         cudaError_t err = cudaSuccess;
-        if (launch_decode_ms_tm_wide(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err))
+        if (launch_decode_ms_tm_wide(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err,
+                                     front))
             return err;
-        if (launch_decode_ms_tc(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err))
+        if (launch_decode_ms_tc(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err, front))
             return err;
     }
-    return launch_decode_ms_generic(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream);
+    return launch_decode_ms_generic(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, front);
+}
+
+bool front_supported(int kind, int llr_type) {
+    if (kind == kFrontNone) return llr_type >= 0 && llr_type < kNumLlrTypes;
+    if (kind == kFrontSoftF32) return llr_type == kI8 || llr_type == kI16;
+    if (kind == kFrontHard) return llr_type == kI8;
+    return false;
 }
 
 const char *decode_ms_kernel_name(int code, int llr_type) {

@@ -24,6 +24,20 @@ inline size_t llr_size(int t) {
     }
 }
 
+// Input front end of decode_ms (see front.cuh): what the `llrs` pointer of a launch holds.
+enum FrontKind : int { kFrontNone = 0, kFrontSoftF32 = 1, kFrontHard = 2 };
+struct Front {
+    int kind = kFrontNone;
+    float scale = 1.0f;   // kFrontSoftF32: llr = clamp(rint(soft * scale), -limit, limit)
+    float limit = 0.0f;
+};
+inline size_t front_frame_bytes(const Front &f, int n, int llr_type) {
+    if (f.kind == kFrontSoftF32) return (size_t)n * 4;
+    if (f.kind == kFrontHard) return (size_t)n / 8;
+    return (size_t)n * llr_size(llr_type);
+}
+bool front_supported(int kind, int llr_type);   // fused kernels exist for (soft, i8|i16) and (hard, i8)
+
 // Device-resident tables of one code (built once per device by DeviceCtx).
 struct DeviceCode {
     int n, k, p, m, b;
@@ -58,7 +72,7 @@ void count_launch(int n = 1);
 // ---- kernel launchers (device pointers, stream-ordered, no synchronisation) ----
 cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
                              size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters,
-                             cudaStream_t stream);
+                             cudaStream_t stream, const Front &front = Front());
 const char *decode_ms_kernel_name(int code, int llr_type);
 
 cudaError_t launch_decode_bf(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
@@ -70,6 +84,9 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
 
 cudaError_t launch_hard_to_llrs(DeviceCtx &ctx, int code, int llr_type, const uint8_t *input, void *llrs,
                                 size_t batch, cudaStream_t stream);
+// llrs[i] = clamp(rint(soft[i] * scale), -limit, limit) as i8 / i16 (the un-fused form of kFrontSoftF32).
+cudaError_t launch_quantise(DeviceCtx &ctx, int code, int llr_type, const float *soft, void *llrs, size_t batch,
+                            float scale, float limit, cudaStream_t stream);
 cudaError_t launch_llrs_to_hard(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
                                 size_t batch, cudaStream_t stream);
 

@@ -46,3 +46,24 @@ def hard_frames(oracle, code, batch, flips, seed):
         for p in pos:
             rx[f, p // 8] ^= 1 << (7 - (p % 8))
     return data, cw, rx
+
+
+def quantise_soft(soft, scale, limit, dtype):
+    """Restatement of the library's soft front end (csrc/front.cuh): everything in float32,
+    product NaN -> 0, round half to even, clamp to +-limit."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        p = soft.astype(np.float32) * np.float32(scale)
+    p = np.where(np.isnan(p), np.float32(0), p)
+    return np.clip(np.rint(p), -limit, limit).astype(dtype)
+
+
+def soft_frames(oracle, code, batch, ebn0_db, seed):
+    """float32 channel LLRs with the awkward values sprinkled in: NaN, +-inf, exact .5 ties, huge magnitudes."""
+    _, cw, llr = make_frames(oracle, code, batch, ebn0_db, seed, ty="f32")
+    rng = np.random.default_rng(seed + 7)
+    flat = llr.reshape(-1)
+    idx = rng.choice(flat.size, size=min(flat.size // 50, 4000), replace=False)
+    specials = np.array([np.nan, np.inf, -np.inf, 0.125, -0.125, 0.375, -0.375, 0.625, 1e30, -1e30, 0.0, -0.0,
+                         7.875, -7.875, 31.5 / 4, 1e-40], dtype=np.float32)
+    flat[idx] = specials[rng.integers(0, specials.size, idx.size)]
+    return cw, llr

@@ -126,6 +126,20 @@ def test_argument_validation_needs_no_gpu(ldpc):
     assert L.labrador_ldpc_copy_encode_batch(0, None, p, 1) == -2
     assert L.labrador_ldpc_decode_ms_batch_async(0, 7, p, p, 1, 10, p, None, None) == -5   # bad llr type
     assert b"llr_type" in L.labrador_ldpc_last_error()
+    # fused front ends: limit / scale / (front, type) combinations are checked before any pointer is touched
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, p, 4.0, 0, p, 1, 10, p, None) == -5
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, p, 4.0, 128, p, 1, 10, p, None) == -5
+    assert L.labrador_ldpc_decode_ms_i16_soft_batch(0, p, 4.0, 32768, p, 1, 10, p, None) == -5
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, p, float("inf"), 31, p, 1, 10, p, None) == -5
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, p, float("nan"), 31, p, 1, 10, p, None) == -5
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(9, p, 4.0, 31, p, 1, 10, p, None) == -1
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, None, 4.0, 31, p, 1, 10, p, None) == -2
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, None, 4.0, 31, None, 0, 10, None, None) == 0
+    assert L.labrador_ldpc_decode_ms_front_batch_async(0, 3, 1, p, 4.0, 31, p, 1, 10, p, None, None) == -5   # soft -> f32
+    assert L.labrador_ldpc_decode_ms_front_batch_async(0, 1, 2, p, 4.0, 31, p, 1, 10, p, None, None) == -5   # hard -> i16
+    assert L.labrador_ldpc_decode_ms_front_batch_async(0, 0, 3, p, 4.0, 31, p, 1, 10, p, None, None) == -5   # bad front
+    assert L.labrador_ldpc_quantise_i8_batch(0, p, 4.0, 200, p, 1) == -5
+    assert L.labrador_ldpc_quantise_batch_async(0, 3, p, 4.0, 31, p, 1, None) == -5
 
 
 def test_python_mirror_length_asserts(ldpc):
