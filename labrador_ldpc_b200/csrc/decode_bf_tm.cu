@@ -1,4 +1,4 @@
-// Bit-packed bit-flipping decoder for the TM codes: one codeword per WARP.
+// Bit-packed bit-flipping decoder for the TM codes: one codeword per group of min(32, M/32) lanes.
 //
 // Replaces LDPCCode::decode_bf (reference src/decoder.rs:243-301) and the erasure pre-pass
 // decode_erasures (src/decoder.rs:144-223) for TM1280 ... TM8192.  Everything those two functions
@@ -7,10 +7,17 @@
 //   * hard decisions and check parities are bit-packed (bit i of word w = element 32w + i);
 //   * the parity of 32 consecutive checks of a block row is the XOR, over the row's blocks, of a
 //     32-bit window of the variable bits -- an aligned word for identity blocks, a funnel shift of
-//     two words for pi_k blocks (quarter q -> (theta+q) mod 4, offset x -> (phi_q + x) mod Q,
+//     two neighbouring words for pi_k blocks (quarter q -> (theta+q) mod 4, offset x -> (phi_q + x) mod Q,
 //     reference src/codes/mod.rs:312-322), and the other way round for the violated-check counts;
-//   * the per-variable violation counts (<= 6) are bit-sliced 3-bit counters; "flip every variable
-//     whose count equals the maximum" (src/decoder.rs:276-296) is a presence mask reduced over the warp.
+//   * every word is stored twice, in lo[] at its own index and in hi[] at its cyclic predecessor's index
+//     inside the quarter, so a window is lo[i] : hi[i] with ONE address; where the window starts (word
+//     index, bit shift) depends only on the block and on the lane's word, and is kept in registers for
+//     the whole launch; all shared accesses of a warp are bank-conflict free;
+//   * the per-variable violation counts (<= 6) come out of a carry-save adder tree as three bit planes;
+//     "flip every variable whose count equals the maximum" (src/decoder.rs:276-296) needs only the set
+//     of counts that occur, OR-accumulated per count and reduced over the codeword's lanes.
+// Codes with fewer than 32 words per block column put 32 / (M/32) codewords in one warp, so every lane
+// owns a word; a codeword that has finished idles (no flips) until the rest of its warp is done.
 // Erasure pre-pass: as written in the reference it always runs exactly one pass when max_iters >= 1
 // and contributes 0 iterations (see decode_bf.cu).  In every TM prototype only the row-2 checks have
 // exactly ONE punctured neighbour (through the identity block in the punctured column), so the single
@@ -27,6 +34,7 @@ using namespace tm;
 namespace {
 
 constexpr int kBfWarps = 8;
+constexpr int kBfClaim = 8;      // most codeword groups a warp claims per atomic (one hot counter for > 1e9 codewords/s)
 
 template <class P> __host__ __device__ constexpr int blocks_in_row_col(int r, int c) {
     int n = 0;
@@ -34,155 +42,235 @@ template <class P> __host__ __device__ constexpr int blocks_in_row_col(int r, in
     return n;
 }
 
+// shared-memory words per codeword: lo[] + hi[], padded so the codewords of one warp start LPC banks apart
+template <class P, int M> __host__ __device__ constexpr int bf_cw_stride() {
+    constexpr int MW = M / 32, LPC = MW < 32 ? MW : 32;
+    constexpr int words = 2 * (P::NCOL + P::NROW) * MW;
+    return LPC == 32 ? words : ((words + 31) / 32) * 32 + LPC;
+}
+
 __device__ __forceinline__ uint32_t load_be32(const uint8_t *p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+
+// sum of up to three / six one-bit planes as bit planes a0 (1), a1 (2), a2 (4): carry-save adders
+__device__ __forceinline__ void full_add(uint32_t x, uint32_t y, uint32_t z, uint32_t &s, uint32_t &c) {
+    s = x ^ y ^ z;
+    c = (x & y) | (z & (x | y));
+}
+template <int DEG>
+__device__ __forceinline__ void count_planes(const uint32_t (&x)[6], uint32_t &a0, uint32_t &a1, uint32_t &a2) {
+    static_assert(DEG >= 1 && DEG <= 6, "variable degrees of the TM prototypes");
+    if constexpr (DEG <= 3) {
+        full_add(x[0], DEG > 1 ? x[1] : 0u, DEG > 2 ? x[2] : 0u, a0, a1);
+        a2 = 0u;
+    } else {
+        uint32_t s1, c1, s2, c2;
+        full_add(x[0], x[1], x[2], s1, c1);
+        full_add(x[3], DEG > 4 ? x[4] : 0u, DEG > 5 ? x[5] : 0u, s2, c2);
+        a0 = s1 ^ s2;
+        full_add(c1, c2, s1 & s2, a1, a2);
+    }
 }
 
 template <int RATE, int M>
 __global__ void __launch_bounds__(32 * kBfWarps)
 decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint8_t *__restrict__ out_all,
                     unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
-                    uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter) {
+                    uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter, const int claim_groups) {
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW, CP = NCOL - 1;
+    constexpr int NP = count_p<P>(NB);
     constexpr int Q = M / 4, QW = Q / 32;                 // words per quarter
     constexpr int MW = M / 32;                            // words per block row / column
+    constexpr int LPC = MW < 32 ? MW : 32;                // lanes per codeword
+    constexpr int CWW = 32 / LPC;                         // codewords per warp
+    constexpr int WPL = MW / LPC;                         // words per lane per block column
     constexpr int NVW = NCOL * MW, NW = (NCOL - 1) * MW, NCW = NROW * MW;
-    constexpr int WPL = (MW + 31) / 32;                   // words per lane per block column
+    constexpr int CWORDS = NVW + NCW;                     // (word, successor) pairs per codeword
     constexpr unsigned kFull = 0xFFFFFFFFu;
-    static_assert(Q % 32 == 0, "quarters are whole words");
+    static_assert(Q % 32 == 0 && (QW & (QW - 1)) == 0 && MW % LPC == 0, "quarters are whole words");
     static_assert(blocks_in_row_col<P>(0, CP) == 2 && blocks_in_row_col<P>(1, CP) == 3 &&
                   blocks_in_row_col<P>(2, CP) == 1 && P::blk(NB - 1).row == 2 && P::blk(NB - 1).col == CP &&
                   !P::blk(NB - 1).isp, "only row 2 votes in the erasure pass, through an identity block");
 
+    // per codeword: lo[CWORDS] then hi[CWORDS] (hard decisions first, then parities); the stride between the
+    // codewords of one warp is LPC mod 32 words so their lanes fall into disjoint banks
+    constexpr int STRIDE = bf_cw_stride<P, M>();
     extern __shared__ __align__(16) uint32_t smem_bf[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *bits = smem_bf + warp * (NVW + NCW);        // [NVW] hard decisions
-    uint32_t *par = bits + NVW;                            // [NCW] check parities
+    const int grp = lane / LPC, wl = lane % LPC;
+    uint32_t *lo = smem_bf + (warp * CWW + grp) * STRIDE;
+    uint32_t *hi = lo + CWORDS;
 
+    // windows of this lane's words: (word index << 5) | bit shift.
+    // direction 0 = check word -> variable bits, direction 1 = variable word -> check parities
+    uint32_t win[2][NP > 0 ? NP : 1][WPL];
+#pragma unroll
+    for (int wi = 0; wi < WPL; wi++) {
+        const int e0 = (wl + wi * LPC) * 32, qa = e0 / Q, off = e0 % Q;
+        static_for<0, NB>([&](auto bi) {
+            constexpr int b = decltype(bi)::value;
+            if constexpr (P::blk(b).isp) {
+                constexpr int ps = count_p<P>(b);
+                const int qv = ((int)prm.theta[b] + qa) & 3;
+                const int s0 = ((int)prm.phi[b][qa] + off) & (Q - 1);
+                win[0][ps][wi] = (uint32_t)(((P::blk(b).col * MW + qv * QW + (s0 >> 5)) << 5) | (s0 & 31));
+                const int q = (qa - (int)prm.theta[b]) & 3;
+                const int s1 = (off - (int)prm.phi[b][q]) & (Q - 1);
+                win[1][ps][wi] = (uint32_t)(((NVW + P::blk(b).row * MW + q * QW + (s1 >> 5)) << 5) | (s1 & 31));
+            }
+        });
+    }
+
+    // word w of an array starting at index `base`: lo[] at its own place, hi[] at its predecessor's
+    auto store_word = [&](int base, int w, uint32_t v) {
+        lo[base + w] = v;
+        hi[base + ((w & ~(QW - 1)) | ((w - 1) & (QW - 1)))] = v;
+    };
+    auto window = [&](uint32_t t) {
+        const uint32_t i = t >> 5;
+        return __funnelshift_r(lo[i], hi[i], t);          // the shift is t mod 32
+    };
     // parity word `w` (0..MW-1) of block row r from the current bits
-    auto row_parity = [&](auto ri, int w) {
+    auto row_parity = [&](auto ri, int wi) {
         constexpr int r = decltype(ri)::value;
-        const int i0 = w * 32, q = i0 / Q, iq0 = i0 % Q;
         uint32_t x = 0;
         static_for<0, NB>([&](auto bi) {
             constexpr int b = decltype(bi)::value;
             if constexpr (P::blk(b).row == r) {
-                constexpr int col = P::blk(b).col;
-                if constexpr (P::blk(b).isp) {
-                    const int qv = ((int)prm.theta[b] + q) & 3;
-                    const int s = ((int)prm.phi[b][q] + iq0) & (Q - 1);
-                    const int base = col * MW + qv * QW;
-                    const int w0 = s >> 5, w1 = (w0 + 1) & (QW - 1);
-                    x ^= __funnelshift_r(bits[base + w0], bits[base + w1], s & 31);
-                } else {
-                    x ^= bits[col * MW + w];
-                }
+                if constexpr (P::blk(b).isp) x ^= window(win[0][count_p<P>(b)][wi]);
+                else x ^= lo[P::blk(b).col * MW + wl + wi * LPC];
             }
         });
         return x;
     };
 
     for (;;) {
-        unsigned long long frame = 0;
-        if (lane == 0) frame = atomicAdd(counter, 1ull);
-        frame = __shfl_sync(kFull, frame, 0);
-        if (frame >= batch) break;
-        const uint8_t *in = in_all + frame * (unsigned long long)(NW * 4);
-        // output[..n/8] = input (:251); punctured bits start as zero (:167)
-        for (int w = lane; w < NVW; w += 32) bits[w] = w < NW ? __brev(load_be32(in + 4 * w)) : 0u;
-        __syncwarp();
-
-        if (max_iters > 0) {
-            // erasure pass: punctured bit j <- parity of row-2 check j over the transmitted bits (:177-213)
-            for (int w = lane; w < MW; w += 32) par[w] = row_parity(std::integral_constant<int, 2>{}, w);
-            __syncwarp();
-            for (int w = lane; w < MW; w += 32) bits[CP * MW + w] = par[w];
-            __syncwarp();
-        }
-
-        unsigned iters_run = max_iters;
-        bool ok = false;
-        for (unsigned iter = 0; iter < max_iters; iter++) {
-            // parity of every check (:269-273)
-            static_for<0, NROW>([&](auto ri) {
-                constexpr int r = decltype(ri)::value;
-                for (int w = lane; w < MW; w += 32) par[r * MW + w] = row_parity(ri, w);
-            });
-            __syncwarp();
-            // violated-check count of every variable, bit-sliced (:276-286)
-            uint32_t c0[NCOL][WPL], c1[NCOL][WPL], c2[NCOL][WPL];
-            uint32_t present = 0;                       // bit v set: some variable has count v
-            static_for<0, NCOL>([&](auto ci) {
-                constexpr int c = decltype(ci)::value;
+        unsigned long long claim = 0;
+        if (lane == 0) claim = atomicAdd(counter, (unsigned long long)(CWW * claim_groups));
+        claim = __shfl_sync(kFull, claim, 0);
+        if (claim >= batch) break;
+        for (int ci = 0; ci < claim_groups; ci++) {
+            const unsigned long long first = claim + (unsigned long long)(ci * CWW);
+            if (first >= batch) break;
+            const unsigned long long frame = first + grp;
+            const bool live = frame < batch;              // the last warp's trailing groups may not exist
+            const uint8_t *in = in_all + (live ? frame : first) * (unsigned long long)(NW * 4);
+            const bool in_aligned = (reinterpret_cast<uintptr_t>(in_all) & 3u) == 0;
+            // output[..n/8] = input (:251); punctured bits start as zero (:167)
 #pragma unroll
-                for (int wi = 0; wi < WPL; wi++) {
-                    const int w = lane + wi * 32;
-                    uint32_t a0 = 0, a1 = 0, a2 = 0;
-                    if (w < MW) {
-                        const int j0 = w * 32, qv = j0 / Q, jq0 = j0 % Q;
+            for (int wi = 0; wi < WPL; wi++) {
+                const int w = wl + wi * LPC;
+#pragma unroll
+                for (int c = 0; c < NCOL; c++) {
+                    uint32_t v = 0;
+                    if (c < NCOL - 1) {
+                        const int iw = c * MW + w;
+                        v = in_aligned ? __byte_perm(reinterpret_cast<const uint32_t *>(in)[iw], 0, 0x0123)
+                                       : load_be32(in + 4 * iw);
+                        v = __brev(v);
+                    }
+                    store_word(c * MW, w, v);
+                }
+            }
+            __syncwarp();
+
+            if (max_iters > 0) {
+                // erasure pass: punctured bit j <- parity of row-2 check j over the transmitted bits (:177-213)
+                uint32_t e[WPL];
+#pragma unroll
+                for (int wi = 0; wi < WPL; wi++) e[wi] = row_parity(std::integral_constant<int, 2>{}, wi);
+                __syncwarp();
+#pragma unroll
+                for (int wi = 0; wi < WPL; wi++) store_word(CP * MW, wl + wi * LPC, e[wi]);
+                __syncwarp();
+            }
+
+            unsigned iters_run = max_iters;
+            bool ok = false, done = !live;
+            for (unsigned iter = 0; iter < max_iters; iter++) {
+                // parity of every check (:269-273)
+                static_for<0, NROW>([&](auto ri) {
+                    constexpr int r = decltype(ri)::value;
+#pragma unroll
+                    for (int wi = 0; wi < WPL; wi++) store_word(NVW + r * MW, wl + wi * LPC, row_parity(ri, wi));
+                });
+                __syncwarp();
+                // violated-check count of every variable as bit planes (:276-286), and which counts occur
+                uint32_t c0[NCOL][WPL], c1[NCOL][WPL], c2[NCOL][WPL];
+                uint32_t occurs[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};       // occurs[v] != 0: some variable has count v
+                static_for<0, NCOL>([&](auto ci2) {
+                    constexpr int c = decltype(ci2)::value;
+                    constexpr int DEG = col_degree<P>(c);
+#pragma unroll
+                    for (int wi = 0; wi < WPL; wi++) {
+                        const int w = wl + wi * LPC;
+                        uint32_t x[6] = {0u, 0u, 0u, 0u, 0u, 0u};
                         static_for<0, NB>([&](auto bi) {
                             constexpr int b = decltype(bi)::value;
                             if constexpr (P::blk(b).col == c) {
-                                constexpr int r = P::blk(b).row;
-                                uint32_t x;
-                                if constexpr (P::blk(b).isp) {
-                                    const int q = (qv - (int)prm.theta[b]) & 3;
-                                    const int s = (jq0 - (int)prm.phi[b][q]) & (Q - 1);
-                                    const int base = r * MW + q * QW;
-                                    const int w0 = s >> 5, w1 = (w0 + 1) & (QW - 1);
-                                    x = __funnelshift_r(par[base + w0], par[base + w1], s & 31);
-                                } else {
-                                    x = par[r * MW + w];
-                                }
-                                const uint32_t t0 = a0 & x;
-                                a0 ^= x;
-                                const uint32_t t1 = a1 & t0;
-                                a1 ^= t0;
-                                a2 ^= t1;
+                                if constexpr (P::blk(b).isp) x[pos_in_col<P>(b)] = window(win[1][count_p<P>(b)][wi]);
+                                else x[pos_in_col<P>(b)] = lo[NVW + P::blk(b).row * MW + w];
                             }
                         });
-                        // which counts occur in this word
-                        const uint32_t n0 = ~a0, n1 = ~a1, n2 = ~a2;
-                        present |= ((n2 & n1 & n0) ? 1u : 0u) | ((n2 & n1 & a0) ? 2u : 0u) | ((n2 & a1 & n0) ? 4u : 0u) |
-                                   ((n2 & a1 & a0) ? 8u : 0u) | ((a2 & n1 & n0) ? 16u : 0u) | ((a2 & n1 & a0) ? 32u : 0u) |
-                                   ((a2 & a1 & n0) ? 64u : 0u) | ((a2 & a1 & a0) ? 128u : 0u);
+                        uint32_t a0, a1, a2;
+                        count_planes<DEG>(x, a0, a1, a2);
+                        c0[c][wi] = a0; c1[c][wi] = a1; c2[c][wi] = a2;
+#pragma unroll
+                        for (int v = 1; v <= DEG; v++)
+                            occurs[v] |= ((v & 1) ? a0 : ~a0) & ((v & 2) ? a1 : ~a1) & ((v & 4) ? a2 : ~a2);
                     }
-                    c0[c][wi] = a0; c1[c][wi] = a1; c2[c][wi] = a2;
+                });
+                uint32_t present = 1u;
+#pragma unroll
+                for (int v = 1; v <= 6; v++) present |= occurs[v] ? (1u << v) : 0u;
+#pragma unroll
+                for (int d = 1; d < LPC; d <<= 1) present |= __shfl_xor_sync(kFull, present, d);
+                const int max_viol = 31 - __clz((int)present);
+                if (max_viol == 0 && !done) { ok = true; iters_run = iter; done = true; }   // :288-289
+                if (__all_sync(kFull, done)) break;
+                // flip every variable whose count equals the maximum (:292-296); finished codewords stay as they are
+                if (!done) {
+                    const uint32_t m0 = (max_viol & 1) ? kFull : 0u, m1 = (max_viol & 2) ? kFull : 0u,
+                                   m2 = (max_viol & 4) ? kFull : 0u;
+                    static_for<0, NCOL>([&](auto ci2) {
+                        constexpr int c = decltype(ci2)::value;
+#pragma unroll
+                        for (int wi = 0; wi < WPL; wi++) {
+                            const int w = wl + wi * LPC;
+                            const uint32_t flip = ~((c0[c][wi] ^ m0) | (c1[c][wi] ^ m1) | (c2[c][wi] ^ m2));
+                            store_word(c * MW, w, lo[c * MW + w] ^ flip);
+                        }
+                    });
                 }
-            });
-            present = __reduce_or_sync(kFull, present);
-            const int max_viol = 31 - __clz((int)present);
-            if (max_viol == 0) { ok = true; iters_run = iter; break; }          // :288-289
-            // flip every variable whose count equals the maximum (:292-296)
-            const uint32_t m0 = (max_viol & 1) ? kFull : 0u, m1 = (max_viol & 2) ? kFull : 0u, m2 = (max_viol & 4) ? kFull : 0u;
-            static_for<0, NCOL>([&](auto ci) {
-                constexpr int c = decltype(ci)::value;
+                __syncwarp();
+            }
+
+            if (live) {
+                uint8_t *out = out_all + frame * (unsigned long long)(NVW * 4);
+                const bool aligned = (reinterpret_cast<uintptr_t>(out_all) & 3u) == 0;
 #pragma unroll
                 for (int wi = 0; wi < WPL; wi++) {
-                    const int w = lane + wi * 32;
-                    if (w < MW) bits[c * MW + w] ^= ~((c0[c][wi] ^ m0) | (c1[c][wi] ^ m1) | (c2[c][wi] ^ m2));
+#pragma unroll
+                    for (int c = 0; c < NCOL; c++) {
+                        const int w = c * MW + wl + wi * LPC;
+                        const uint32_t rev = __brev(lo[w]);
+                        if (aligned) {
+                            reinterpret_cast<uint32_t *>(out)[w] = __byte_perm(rev, 0, 0x0123);
+                        } else {
+                            out[4 * w + 0] = (uint8_t)(rev >> 24); out[4 * w + 1] = (uint8_t)(rev >> 16);
+                            out[4 * w + 2] = (uint8_t)(rev >> 8);  out[4 * w + 3] = (uint8_t)rev;
+                        }
+                    }
                 }
-            });
+                if (wl == 0) {
+                    if (success) success[frame] = ok ? 1 : 0;
+                    if (iters_out) iters_out[frame] = iters_run;
+                }
+            }
             __syncwarp();
         }
-
-        uint8_t *out = out_all + frame * (unsigned long long)(NVW * 4);
-        const bool aligned = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-        for (int w = lane; w < NVW; w += 32) {
-            const uint32_t rev = __brev(bits[w]);
-            if (aligned) {
-                reinterpret_cast<uint32_t *>(out)[w] = __byte_perm(rev, 0, 0x0123);
-            } else {
-                out[4 * w + 0] = (uint8_t)(rev >> 24); out[4 * w + 1] = (uint8_t)(rev >> 16);
-                out[4 * w + 2] = (uint8_t)(rev >> 8);  out[4 * w + 3] = (uint8_t)rev;
-            }
-        }
-        if (lane == 0) {
-            if (success) success[frame] = ok ? 1 : 0;
-            if (iters_out) iters_out[frame] = iters_run;
-        }
-        __syncwarp();
     }
 }
 
@@ -191,7 +279,8 @@ cudaError_t launch_bf_tm(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
                          size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     typedef Proto<RATE> P;
     const TmParams prm = make_params<RATE>(c);
-    const size_t smem = (size_t)kBfWarps * (P::NCOL + P::NROW) * (M / 32) * sizeof(uint32_t);
+    constexpr int MW = M / 32, CWW = MW < 32 ? 32 / MW : 1;            // codewords per warp
+    const size_t smem = (size_t)kBfWarps * CWW * bf_cw_stride<P, M>() * sizeof(uint32_t);
     auto kern = decode_bf_tm_kernel<RATE, M>;
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
@@ -204,14 +293,19 @@ cudaError_t launch_bf_tm(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
-    const unsigned long long need = (batch + kBfWarps - 1) / kBfWarps;
+    // large batches claim several groups per atomic; small ones keep one group per claim so every SM gets work
+    const unsigned long long groups = (batch + CWW - 1) / CWW;
+    unsigned long long claim = groups / (grid * kBfWarps * 4);
+    claim = claim < 1 ? 1 : (claim > kBfClaim ? kBfClaim : claim);
+    const unsigned long long per_cta = (unsigned long long)kBfWarps * claim;
+    const unsigned long long need = (groups + per_cta - 1) / per_cta;
     if (grid > need) grid = need;
     unsigned long long *counter = nullptr;
     e = next_counter(ctx.device, stream, &counter);
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kBfWarps, smem, stream>>>(prm, input, output, (unsigned long long)batch, mi, success,
-                                                          iters, counter);
+                                                          iters, counter, (int)claim);
     count_launch();
     return cudaGetLastError();
 }

@@ -61,6 +61,17 @@ pub mod ffi {
         pub fn labrador_ldpc_llrs_to_hard_i32_batch(code: LDPCCode, llrs: *const i32, output: *mut u8, batch: usize) -> c_int;
         pub fn labrador_ldpc_llrs_to_hard_f32_batch(code: LDPCCode, llrs: *const f32, output: *mut u8, batch: usize) -> c_int;
         pub fn labrador_ldpc_llrs_to_hard_f64_batch(code: LDPCCode, llrs: *const f64, output: *mut u8, batch: usize) -> c_int;
+        // fused front ends (include/labrador_ldpc.h, "Fused front ends of decode_ms")
+        pub fn labrador_ldpc_decode_ms_i8_soft_batch(code: LDPCCode, soft: *const f32, scale: f32, limit: c_int,
+            output: *mut u8, batch: usize, max_iters: usize, success: *mut u8, iters_run: *mut u32) -> c_int;
+        pub fn labrador_ldpc_decode_ms_i16_soft_batch(code: LDPCCode, soft: *const f32, scale: f32, limit: c_int,
+            output: *mut u8, batch: usize, max_iters: usize, success: *mut u8, iters_run: *mut u32) -> c_int;
+        pub fn labrador_ldpc_decode_ms_i8_hard_batch(code: LDPCCode, input: *const u8, output: *mut u8, batch: usize,
+            max_iters: usize, success: *mut u8, iters_run: *mut u32) -> c_int;
+        pub fn labrador_ldpc_quantise_i8_batch(code: LDPCCode, soft: *const f32, scale: f32, limit: c_int,
+            llrs: *mut i8, batch: usize) -> c_int;
+        pub fn labrador_ldpc_quantise_i16_batch(code: LDPCCode, soft: *const f32, scale: f32, limit: c_int,
+            llrs: *mut i16, batch: usize) -> c_int;
     }
 }
 
@@ -184,5 +195,29 @@ impl LDPCCode {
         assert_eq!(output.len(), batch * self.output_len());
         check(unsafe { ffi::labrador_ldpc_decode_bf_batch(self, input.as_ptr(), output.as_mut_ptr(), batch, maxiters,
                                                          success.as_mut_ptr(), iters.as_mut_ptr()) })
+    }
+
+    /// decode_ms::<i8> of `clamp(round(soft * scale), -limit, limit)`, quantised inside the decoder.
+    pub fn decode_ms_soft_i8_batch(self, soft: &[f32], scale: f32, limit: i8, output: &mut [u8], maxiters: usize,
+                                   success: &mut [u8], iters: &mut [u32]) -> Result<(), Error> {
+        let batch = soft.len() / self.n();
+        assert_eq!(soft.len(), batch * self.n());
+        assert_eq!(output.len(), batch * self.output_len());
+        assert_eq!(success.len(), batch);
+        assert_eq!(iters.len(), batch);
+        check(unsafe { ffi::labrador_ldpc_decode_ms_i8_soft_batch(self, soft.as_ptr(), scale, limit as c_int,
+                                                                 output.as_mut_ptr(), batch, maxiters,
+                                                                 success.as_mut_ptr(), iters.as_mut_ptr()) })
+    }
+    /// decode_ms::<i8> of `hard_to_llrs(input)`, converted inside the decoder.
+    pub fn decode_ms_hard_batch(self, input: &[u8], output: &mut [u8], maxiters: usize,
+                                success: &mut [u8], iters: &mut [u32]) -> Result<(), Error> {
+        let batch = input.len() / (self.n() / 8);
+        assert_eq!(input.len(), batch * self.n() / 8);
+        assert_eq!(output.len(), batch * self.output_len());
+        assert_eq!(success.len(), batch);
+        assert_eq!(iters.len(), batch);
+        check(unsafe { ffi::labrador_ldpc_decode_ms_i8_hard_batch(self, input.as_ptr(), output.as_mut_ptr(), batch,
+                                                                 maxiters, success.as_mut_ptr(), iters.as_mut_ptr()) })
     }
 }
