@@ -49,6 +49,16 @@ template <class P, int M> __host__ __device__ constexpr int bf_cw_stride() {
     return LPC == 32 ? words : ((words + 31) / 32) * 32 + LPC;
 }
 
+// does any permutation block read this block column (row parities) / block row (violation counts)?
+template <class P> __host__ __device__ constexpr bool col_has_p(int c) {
+    for (int b = 0; b < P::NB; b++) if (P::blk(b).col == c && P::blk(b).isp) return true;
+    return false;
+}
+template <class P> __host__ __device__ constexpr bool row_has_p(int r) {
+    for (int b = 0; b < P::NB; b++) if (P::blk(b).row == r && P::blk(b).isp) return true;
+    return false;
+}
+
 __device__ __forceinline__ uint32_t load_be32(const uint8_t *p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
@@ -132,6 +142,9 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
         const uint32_t i = t >> 5;
         return __funnelshift_r(lo[i], hi[i], t);          // the shift is t mod 32
     };
+    // Each lane keeps its own words of the hard decisions (bw) and parities (pw) in registers: identity blocks
+    // connect word w with word w, so only what a permutation block reads has to go through shared memory.
+    uint32_t bw[NCOL][WPL], pw[NROW][WPL];
     // parity word `w` (0..MW-1) of block row r from the current bits
     auto row_parity = [&](auto ri, int wi) {
         constexpr int r = decltype(ri)::value;
@@ -140,7 +153,7 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
             constexpr int b = decltype(bi)::value;
             if constexpr (P::blk(b).row == r) {
                 if constexpr (P::blk(b).isp) x ^= window(win[0][count_p<P>(b)][wi]);
-                else x ^= lo[P::blk(b).col * MW + wl + wi * LPC];
+                else x ^= bw[P::blk(b).col][wi];
             }
         });
         return x;
@@ -171,7 +184,8 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
                                        : load_be32(in + 4 * iw);
                         v = __brev(v);
                     }
-                    store_word(c * MW, w, v);
+                    bw[c][wi] = v;
+                    if (col_has_p<P>(c)) store_word(c * MW, w, v);
                 }
             }
             __syncwarp();
@@ -183,7 +197,7 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
                 for (int wi = 0; wi < WPL; wi++) e[wi] = row_parity(std::integral_constant<int, 2>{}, wi);
                 __syncwarp();
 #pragma unroll
-                for (int wi = 0; wi < WPL; wi++) store_word(CP * MW, wl + wi * LPC, e[wi]);
+                for (int wi = 0; wi < WPL; wi++) { bw[CP][wi] = e[wi]; store_word(CP * MW, wl + wi * LPC, e[wi]); }
                 __syncwarp();
             }
 
@@ -194,7 +208,10 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
                 static_for<0, NROW>([&](auto ri) {
                     constexpr int r = decltype(ri)::value;
 #pragma unroll
-                    for (int wi = 0; wi < WPL; wi++) store_word(NVW + r * MW, wl + wi * LPC, row_parity(ri, wi));
+                    for (int wi = 0; wi < WPL; wi++) {
+                        pw[r][wi] = row_parity(ri, wi);
+                        if constexpr (row_has_p<P>(r)) store_word(NVW + r * MW, wl + wi * LPC, pw[r][wi]);
+                    }
                 });
                 __syncwarp();
                 // violated-check count of every variable as bit planes (:276-286), and which counts occur
@@ -211,7 +228,7 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
                             constexpr int b = decltype(bi)::value;
                             if constexpr (P::blk(b).col == c) {
                                 if constexpr (P::blk(b).isp) x[pos_in_col<P>(b)] = window(win[1][count_p<P>(b)][wi]);
-                                else x[pos_in_col<P>(b)] = lo[NVW + P::blk(b).row * MW + w];
+                                else x[pos_in_col<P>(b)] = pw[P::blk(b).row][wi];
                             }
                         });
                         uint32_t a0, a1, a2;
@@ -238,9 +255,8 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
                         constexpr int c = decltype(ci2)::value;
 #pragma unroll
                         for (int wi = 0; wi < WPL; wi++) {
-                            const int w = wl + wi * LPC;
-                            const uint32_t flip = ~((c0[c][wi] ^ m0) | (c1[c][wi] ^ m1) | (c2[c][wi] ^ m2));
-                            store_word(c * MW, w, lo[c * MW + w] ^ flip);
+                            bw[c][wi] ^= ~((c0[c][wi] ^ m0) | (c1[c][wi] ^ m1) | (c2[c][wi] ^ m2));
+                            if constexpr (col_has_p<P>(c)) store_word(c * MW, wl + wi * LPC, bw[c][wi]);
                         }
                     });
                 }
@@ -255,7 +271,7 @@ decode_bf_tm_kernel(const TmParams prm, const uint8_t *__restrict__ in_all, uint
 #pragma unroll
                     for (int c = 0; c < NCOL; c++) {
                         const int w = c * MW + wl + wi * LPC;
-                        const uint32_t rev = __brev(lo[w]);
+                        const uint32_t rev = __brev(bw[c][wi]);
                         if (aligned) {
                             reinterpret_cast<uint32_t *>(out)[w] = __byte_perm(rev, 0, 0x0123);
                         } else {

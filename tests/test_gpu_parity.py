@@ -268,6 +268,37 @@ def test_decode_bf_random_errors(ldpc, oracle, code):
         assert_exact(got, want, "%s bf maxiters=%d" % (NAMES[code], maxiters))
 
 
+def test_decode_bf_ragged_large_and_unaligned_batches(ldpc, oracle):
+    """The TM bit-flipping kernel packs 32 / (M/32) codewords per warp and claims several groups per
+    atomic on large batches: cover batches that are not a multiple of the group size, a batch large
+    enough for multi-group claims, and device buffers that are not 4-byte aligned."""
+    import torch
+    for code in (3, 4, 5, 8):
+        c = ldpc.LDPCCode(code)
+        for batch in (1, 7, 45):
+            _, _, rx = hard_frames(oracle, code, batch, 4, seed=650 + code + batch)
+            assert_exact(c.decode_bf_batch(rx, 30), oracle.decode_bf_batch(code, rx, 30, nthreads=8),
+                         "%s bf batch=%d" % (NAMES[code], batch))
+        _, _, rx = hard_frames(oracle, code, 33, 5, seed=690 + code)
+        want = oracle.decode_bf_batch(code, rx, 30, nthreads=8)
+        buf = torch.zeros(rx.size + 8, dtype=torch.uint8, device="cuda")
+        obuf = torch.zeros(33 * c.output_len() + 8, dtype=torch.uint8, device="cuda")
+        for off in (1, 2):
+            view = buf[off: off + rx.size].view(rx.shape)
+            view.copy_(torch.from_numpy(rx))
+            oview = obuf[off: off + 33 * c.output_len()].view(33, c.output_len())
+            got = c.decode_bf_batch(view, 30, output=oview)
+            torch.cuda.synchronize()
+            assert_exact([g.cpu().numpy() for g in got], want, "%s bf unaligned off=%d" % (NAMES[code], off))
+    code, batch = 3, 100_000   # > 2 * 148 SMs * 8 warps * 4 * 8 codewords: two groups per claim
+    rng = np.random.default_rng(77)
+    _, _, small = hard_frames(oracle, code, 4096, 3, seed=700)
+    rx = small[rng.integers(0, 4096, batch)]
+    rx[:, 5] ^= rng.integers(0, 256, batch, dtype=np.uint8)       # make the frames differ
+    want = oracle.decode_bf_batch(code, rx, 20, nthreads=8)
+    assert_exact(ldpc.LDPCCode(code).decode_bf_batch(rx, 20), want, "TM1280 bf large batch")
+
+
 @pytest.mark.parametrize("code", [c for c in CODES if c >= 3])
 def test_erasure_prepass_matches_min_sum(ldpc, oracle, code):
     # reference src/decoder.rs:607-645: on a clean codeword the punctured bits recovered by
