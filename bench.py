@@ -33,7 +33,8 @@ EBN0_DB = 2.0
 MAX_ITERS = 100
 N, K_INFO, OUT_LEN, EDGES = 8192, 4096, 1280, 30720
 ALG_BYTES_PER_FRAME = N * 1 + OUT_LEN + 8          # LLRs in + packed output + flags
-NCU_DRAM_BYTES_PER_FRAME = 9399                    # profiles/r01_tm8192_ncu.md (615.98 MB / 65536 frames)
+NCU_DRAM_BYTES_PER_FRAME = 9391                    # profiles/r01_tm8192_ncu.md, final build (615.47 MB / 65536 frames)
+NCU_ALU_PIPE_BUSY = 0.875                          # sm__pipe_alu_cycles_active of the same capture
 WORKLOAD = "TM8192 (k=4096, r=1/2) decode_ms i8 LLRs, Eb/N0 2 dB, max_iters 100"
 
 
@@ -316,7 +317,10 @@ def main():
                              "see roofline_alu"},
         "roofline_alu": {"edge_pass_updates_per_s": edge_updates / world / (ms_per_step * 1e-3),
                          "int_lane_ops_peak_per_s": int_peak,
-                         "note": "per GPU; one edge-pass update = one trip of either edge loop of src/decoder.rs:388-450"},
+                         "alu_pipe_busy_frac_ncu": NCU_ALU_PIPE_BUSY,
+                         "note": "per GPU; one edge-pass update = one trip of either edge loop of src/decoder.rs:388-450; "
+                                 "the binding unit is the integer ALU pipe, 87.5 % busy in the ncu capture "
+                                 "(profiles/r01_tm8192_ncu.md)"},
     }
 
     if not args.no_cpu_baseline:
