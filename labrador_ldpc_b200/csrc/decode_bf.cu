@@ -22,6 +22,9 @@ namespace ldpc {
 bool launch_decode_bf_tm(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
                          size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err);
 
+bool launch_decode_bf_tc(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
+                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err);
+
 namespace {
 
 __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restrict__ in_all,
@@ -127,10 +130,13 @@ __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restric
 cudaError_t launch_decode_bf(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
                              size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     if (batch == 0) return cudaSuccess;
-    {   // TM codes: bit-packed warp-per-codeword kernel (LABRADOR_LDPC_FORCE_GENERIC=1 keeps the table-driven one)
+    {   // bit-packed kernels: lane groups per codeword for the TM codes, one thread per codeword for the TC codes
+        // (LABRADOR_LDPC_FORCE_GENERIC=1 keeps the table-driven kernel below)
         static const bool generic = [] { const char *e = getenv("LABRADOR_LDPC_FORCE_GENERIC"); return e && e[0] == '1'; }();
         cudaError_t err = cudaSuccess;
         if (!generic && launch_decode_bf_tm(ctx, code, input, output, batch, max_iters, success, iters, stream, &err))
+            return err;
+        if (!generic && launch_decode_bf_tc(ctx, code, input, output, batch, max_iters, success, iters, stream, &err))
             return err;
     }
     const DeviceCode &dc = ctx.codes[code];

@@ -25,6 +25,7 @@
 // and 1 have two / three punctured neighbours and never vote.  (static_assert'ed below.)
 #include <cuda_runtime.h>
 
+#include "bf_common.cuh"
 #include "runtime.h"
 #include "tm_common.cuh"
 
@@ -61,26 +62,6 @@ template <class P> __host__ __device__ constexpr bool row_has_p(int r) {
 
 __device__ __forceinline__ uint32_t load_be32(const uint8_t *p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
-}
-
-// sum of up to three / six one-bit planes as bit planes a0 (1), a1 (2), a2 (4): carry-save adders
-__device__ __forceinline__ void full_add(uint32_t x, uint32_t y, uint32_t z, uint32_t &s, uint32_t &c) {
-    s = x ^ y ^ z;
-    c = (x & y) | (z & (x | y));
-}
-template <int DEG>
-__device__ __forceinline__ void count_planes(const uint32_t (&x)[6], uint32_t &a0, uint32_t &a1, uint32_t &a2) {
-    static_assert(DEG >= 1 && DEG <= 6, "variable degrees of the TM prototypes");
-    if constexpr (DEG <= 3) {
-        full_add(x[0], DEG > 1 ? x[1] : 0u, DEG > 2 ? x[2] : 0u, a0, a1);
-        a2 = 0u;
-    } else {
-        uint32_t s1, c1, s2, c2;
-        full_add(x[0], x[1], x[2], s1, c1);
-        full_add(x[3], DEG > 4 ? x[4] : 0u, DEG > 5 ? x[5] : 0u, s2, c2);
-        a0 = s1 ^ s2;
-        full_add(c1, c2, s1 & s2, a1, a2);
-    }
 }
 
 template <int RATE, int M>
