@@ -369,6 +369,36 @@ int labrador_ldpc_quantise_i16_batch(enum labrador_ldpc_code code, const float *
 int labrador_ldpc_quantise_batch_async(enum labrador_ldpc_code code, int llr_type, const float *soft, float scale,
                                        int limit, void *llrs, size_t batch, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------
+ * Harness kernels (not in the reference's library; they replace the per-trial
+ * set-up of its Monte-Carlo driver, perftest/src/main.rs:9-28, on the device).
+ * Random numbers are counter-based: Philox4x32-10 keyed by `seed`, counter =
+ * (frame index, word index, stream), so frame `first_frame + f` gets the same
+ * bits whichever GPU, chunk or call produces it.
+ *   random_data : data[B][k/8], 16 bytes per Philox call (stream 1), words
+ *                 stored little-endian                         (main.rs:10)
+ *   awgn        : y = (1 - 2 bit) + sigma * z, z ~ N(0,1) by Box-Muller on the
+ *                 four words of counter (frame, i/4, stream 2) for variables
+ *                 i..i+3                                       (main.rs:13-18)
+ *                 out_type LABRADOR_LDPC_LLR_F32: out = y * scale
+ *                 out_type ..._I8 / ..._I16: out = clamp(rint(y * scale), +-limit)
+ *   count_errors: bit_errors[f] = popcount(decoded[f][..k/8] ^ data[f])
+ *                 with decoded[B][output_len]                  (main.rs:23-28)
+ * ------------------------------------------------------------------------- */
+int labrador_ldpc_random_data_batch(enum labrador_ldpc_code code, uint64_t seed, uint64_t first_frame,
+                                    uint8_t *data, size_t batch);
+int labrador_ldpc_awgn_batch(enum labrador_ldpc_code code, int out_type, const uint8_t *codewords, float sigma,
+                             float scale, int limit, uint64_t seed, uint64_t first_frame, void *out, size_t batch);
+int labrador_ldpc_count_errors_batch(enum labrador_ldpc_code code, const uint8_t *decoded, const uint8_t *data,
+                                     uint32_t *bit_errors, size_t batch);
+int labrador_ldpc_random_data_batch_async(enum labrador_ldpc_code code, uint64_t seed, uint64_t first_frame,
+                                          uint8_t *data, size_t batch, void *cuda_stream);
+int labrador_ldpc_awgn_batch_async(enum labrador_ldpc_code code, int out_type, const uint8_t *codewords, float sigma,
+                                   float scale, int limit, uint64_t seed, uint64_t first_frame, void *out,
+                                   size_t batch, void *cuda_stream);
+int labrador_ldpc_count_errors_batch_async(enum labrador_ldpc_code code, const uint8_t *decoded, const uint8_t *data,
+                                           uint32_t *bit_errors, size_t batch, void *cuda_stream);
+
 /* Introspection used by the tests and the benchmark harness. */
 /* Number of kernels this library has launched since load (all devices). */
 unsigned long long labrador_ldpc_kernel_launch_count(void);

@@ -95,6 +95,13 @@ lib.labrador_ldpc_quantise_i8_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz]
 lib.labrador_ldpc_quantise_i16_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz]
 lib.labrador_ldpc_quantise_batch_async.argtypes = [_ci, _ci, _vp, _cf, _ci, _vp, _sz, _vp]
 FRONT_NONE, FRONT_SOFT_F32, FRONT_HARD = 0, 1, 2
+_u64 = ctypes.c_uint64
+lib.labrador_ldpc_random_data_batch.argtypes = [_ci, _u64, _u64, _vp, _sz]
+lib.labrador_ldpc_random_data_batch_async.argtypes = [_ci, _u64, _u64, _vp, _sz, _vp]
+lib.labrador_ldpc_awgn_batch.argtypes = [_ci, _ci, _vp, _cf, _cf, _ci, _u64, _u64, _vp, _sz]
+lib.labrador_ldpc_awgn_batch_async.argtypes = [_ci, _ci, _vp, _cf, _cf, _ci, _u64, _u64, _vp, _sz, _vp]
+lib.labrador_ldpc_count_errors_batch.argtypes = [_ci, _vp, _vp, _vp, _sz]
+lib.labrador_ldpc_count_errors_batch_async.argtypes = [_ci, _vp, _vp, _vp, _sz, _vp]
 
 
 def _check(rc):
@@ -374,6 +381,45 @@ class LDPCCode(enum.IntEnum):
             _check(getattr(lib, "labrador_ldpc_quantise_%s_batch" % ty)(int(self), _ptr(soft), float(scale), int(limit),
                                                                         _ptr(llrs), batch))
         return llrs
+
+    # ---- harness kernels (include/labrador_ldpc.h "Harness kernels"; csrc/channel.cu) ----
+    def random_data_batch(self, seed, first_frame, data):
+        """Fill data[B, k/8] with the Philox bytes of frames first_frame .. first_frame+B-1 of run `seed`."""
+        batch = self._batch_of(data, self.k() // 8)
+        stream = _current_stream(data)
+        if stream is not None:
+            _check(lib.labrador_ldpc_random_data_batch_async(int(self), seed, first_frame, _ptr(data), batch, stream))
+        else:
+            _check(lib.labrador_ldpc_random_data_batch(int(self), seed, first_frame, _ptr(data), batch))
+        return data
+
+    def awgn_batch(self, codewords, sigma, scale, seed, first_frame, ty="f32", limit=0, out=None):
+        """BPSK + Gaussian noise: y = (1 - 2 bit) + sigma z; out = y * scale (f32) or its quantisation (i8 / i16)."""
+        batch = self._batch_of(codewords, self.n() // 8)
+        if out is None:
+            out = _alloc_like(codewords, (batch, self.n()), _NP_OF[ty])
+        stream = _current_stream(codewords)
+        if stream is not None:
+            _check(lib.labrador_ldpc_awgn_batch_async(int(self), LLR_TYPES[ty], _ptr(codewords), float(sigma), float(scale),
+                                                      int(limit), seed, first_frame, _ptr(out), batch, stream))
+        else:
+            _check(lib.labrador_ldpc_awgn_batch(int(self), LLR_TYPES[ty], _ptr(codewords), float(sigma), float(scale),
+                                                int(limit), seed, first_frame, _ptr(out), batch))
+        return out
+
+    def count_errors_batch(self, decoded, data, errors=None):
+        """errors[f] = number of wrong bits among the first k/8 bytes of decoded[f] (decoded is [B, output_len])."""
+        batch = self._batch_of(data, self.k() // 8)
+        if self._batch_of(decoded, self.output_len()) != batch:
+            raise ValueError("decoded has the wrong number of frames")
+        if errors is None:
+            errors = _alloc_like(data, (batch,), np.uint32)
+        stream = _current_stream(data)
+        if stream is not None:
+            _check(lib.labrador_ldpc_count_errors_batch_async(int(self), _ptr(decoded), _ptr(data), _ptr(errors), batch, stream))
+        else:
+            _check(lib.labrador_ldpc_count_errors_batch(int(self), _ptr(decoded), _ptr(data), _ptr(errors), batch))
+        return errors
 
     def decode_bf_batch(self, input, maxiters, output=None, success=None, iters=None, stream=None):
         batch = self._batch_of(input, self.n() // 8)

@@ -95,6 +95,84 @@ int quantise_impl(int code, int ty, const float *soft, float scale, int limit, v
     });
 }
 
+int random_data_impl(int code, unsigned long long seed, unsigned long long first_frame, uint8_t *data, size_t batch,
+                     bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (batch == 0) return LDPC_OK;
+    if (!data) return fail(LDPC_ERR_NULL_POINTER, "data must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({data}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_random_data(ctx, code, seed, first_frame, data, batch, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({nullptr, data, (size_t)c->k / 8});
+    return run_host_batch_at(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st,
+                                                size_t first) {
+        return launch_random_data(ctx, code, seed, first_frame + first, static_cast<uint8_t *>(d[0]), nf, st);
+    });
+}
+
+int awgn_impl(int code, int ty, const uint8_t *codewords, float sigma, float scale, int limit, unsigned long long seed,
+              unsigned long long first_frame, void *out, size_t batch, bool async, cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (ty != kI8 && ty != kI16 && ty != kF32) return fail(LDPC_ERR_BAD_ARGUMENT, "channel output is i8, i16 or f32");
+    if (ty != kF32 && (limit < 1 || limit > (ty == kI8 ? 127 : 32767)))
+        return fail(LDPC_ERR_BAD_ARGUMENT, "limit must be in 1..127 (i8) or 1..32767 (i16)");
+    if (!(sigma >= 0.0f) || sigma - sigma != 0.0f || !(scale == scale) || scale - scale != 0.0f)
+        return fail(LDPC_ERR_BAD_ARGUMENT, "sigma must be finite and >= 0, scale finite");
+    if (batch == 0) return LDPC_OK;
+    if (!codewords || !out) return fail(LDPC_ERR_NULL_POINTER, "codewords/out must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({codewords, out}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    const float flimit = (float)limit;
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_awgn(ctx, code, ty, codewords, sigma, scale, flimit, seed, first_frame, out, batch, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({codewords, nullptr, (size_t)c->n / 8});
+    arrays.push_back({nullptr, out, (size_t)c->n * llr_size(ty)});
+    return run_host_batch_at(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st,
+                                                size_t first) {
+        return launch_awgn(ctx, code, ty, static_cast<const uint8_t *>(d[0]), sigma, scale, flimit, seed,
+                           first_frame + first, d[1], nf, st);
+    });
+}
+
+int count_errors_impl(int code, const uint8_t *decoded, const uint8_t *data, uint32_t *errors, size_t batch, bool async,
+                      cudaStream_t stream) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (batch == 0) return LDPC_OK;
+    if (!decoded || !data || !errors) return fail(LDPC_ERR_NULL_POINTER, "decoded/data/errors must not be NULL");
+    int dev = -1;
+    const int kind = common_kind({decoded, data, errors}, &dev);
+    if (async && kind != 1) return fail(LDPC_ERR_MIXED_POINTERS, "_async entry points take device pointers only");
+    if (kind < 0) return fail(LDPC_ERR_MIXED_POINTERS, "pointers must be all host or all on one device");
+    if (kind == 1) {
+        return run_device_batch(dev, stream, !async, [&](DeviceCtx &ctx, cudaStream_t st) {
+            return launch_count_errors(ctx, code, decoded, data, errors, batch, st);
+        });
+    }
+    std::vector<HostArray> arrays;
+    arrays.push_back({decoded, nullptr, c->output_len()});
+    arrays.push_back({data, nullptr, (size_t)c->k / 8});
+    arrays.push_back({nullptr, errors, 4});
+    return run_host_batch(arrays, batch, [=](DeviceCtx &ctx, const std::vector<void *> &d, size_t nf, cudaStream_t st) {
+        return launch_count_errors(ctx, code, static_cast<const uint8_t *>(d[0]), static_cast<const uint8_t *>(d[1]),
+                                   static_cast<uint32_t *>(d[2]), nf, st);
+    });
+}
+
 Front soft_front(float scale, int limit) {
     Front f;
     f.kind = kFrontSoftF32;
@@ -389,6 +467,39 @@ int labrador_ldpc_quantise_i16_batch(enum labrador_ldpc_code code, const float *
 int labrador_ldpc_quantise_batch_async(enum labrador_ldpc_code code, int llr_type, const float *soft, float scale,
                                        int limit, void *llrs, size_t batch, void *cuda_stream) {
     return quantise_impl(code, llr_type, soft, scale, limit, llrs, batch, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+// ---- harness kernels: counter-based frame generator and error counter (csrc/channel.cu) ----
+int labrador_ldpc_random_data_batch(enum labrador_ldpc_code code, uint64_t seed, uint64_t first_frame, uint8_t *data,
+                                    size_t batch) {
+    return random_data_impl(code, seed, first_frame, data, batch, false, nullptr);
+}
+
+int labrador_ldpc_awgn_batch(enum labrador_ldpc_code code, int out_type, const uint8_t *codewords, float sigma,
+                             float scale, int limit, uint64_t seed, uint64_t first_frame, void *out, size_t batch) {
+    return awgn_impl(code, out_type, codewords, sigma, scale, limit, seed, first_frame, out, batch, false, nullptr);
+}
+
+int labrador_ldpc_count_errors_batch(enum labrador_ldpc_code code, const uint8_t *decoded, const uint8_t *data,
+                                     uint32_t *bit_errors, size_t batch) {
+    return count_errors_impl(code, decoded, data, bit_errors, batch, false, nullptr);
+}
+
+int labrador_ldpc_random_data_batch_async(enum labrador_ldpc_code code, uint64_t seed, uint64_t first_frame,
+                                          uint8_t *data, size_t batch, void *cuda_stream) {
+    return random_data_impl(code, seed, first_frame, data, batch, true, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int labrador_ldpc_awgn_batch_async(enum labrador_ldpc_code code, int out_type, const uint8_t *codewords, float sigma,
+                                   float scale, int limit, uint64_t seed, uint64_t first_frame, void *out, size_t batch,
+                                   void *cuda_stream) {
+    return awgn_impl(code, out_type, codewords, sigma, scale, limit, seed, first_frame, out, batch, true,
+                     static_cast<cudaStream_t>(cuda_stream));
+}
+
+int labrador_ldpc_count_errors_batch_async(enum labrador_ldpc_code code, const uint8_t *decoded, const uint8_t *data,
+                                           uint32_t *bit_errors, size_t batch, void *cuda_stream) {
+    return count_errors_impl(code, decoded, data, bit_errors, batch, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
 unsigned long long labrador_ldpc_kernel_launch_count(void) { return launch_count(); }

@@ -302,7 +302,7 @@ size_t chunk_bytes_target() {
 }
 
 int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<HostArray> &arrays, size_t first,
-                            size_t count, const BatchLaunch &launch) {
+                            size_t count, const BatchLaunchAt &launch) {
     std::lock_guard<std::mutex> lock(mu);
     CUDA_TRY(cudaSetDevice(ctx.device));
     size_t per_frame = 0;
@@ -347,7 +347,7 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
             }
         }
         if (rc != LDPC_OK) break;
-        cudaError_t e = launch(ctx, dptr, nf, st);
+        cudaError_t e = launch(ctx, dptr, nf, st, f0);
         if (e != cudaSuccess) { rc = cuda_error(e, "kernel launch"); break; }
         for (size_t i = 0; i < arrays.size(); i++) {
             const HostArray &a = arrays[i];
@@ -367,7 +367,7 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
 
 }  // namespace
 
-int run_host_batch(const std::vector<HostArray> &arrays, size_t batch, const BatchLaunch &launch) {
+int run_host_batch_at(const std::vector<HostArray> &arrays, size_t batch, const BatchLaunchAt &launch) {
     if (batch == 0) return LDPC_OK;
     int rc = runtime_init(nullptr, 0);
     if (rc != LDPC_OK) return rc;

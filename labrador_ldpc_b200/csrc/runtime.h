@@ -90,4 +90,14 @@ cudaError_t launch_quantise(DeviceCtx &ctx, int code, int llr_type, const float 
 cudaError_t launch_llrs_to_hard(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output,
                                 size_t batch, cudaStream_t stream);
 
+// ---- harness kernels (channel.cu): counter-based frame generator and error counter ----
+cudaError_t launch_random_data(DeviceCtx &ctx, int code, unsigned long long seed, unsigned long long first_frame,
+                               uint8_t *data, size_t batch, cudaStream_t stream);
+// out_type kF32: out = y * scale;  kI8 / kI16: out = clamp(rint(y * scale), -limit, limit);  y = (1 - 2 bit) + sigma * z
+cudaError_t launch_awgn(DeviceCtx &ctx, int code, int out_type, const uint8_t *codewords, float sigma, float scale,
+                        float limit, unsigned long long seed, unsigned long long first_frame, void *out, size_t batch,
+                        cudaStream_t stream);
+cudaError_t launch_count_errors(DeviceCtx &ctx, int code, const uint8_t *decoded, const uint8_t *data, uint32_t *errors,
+                                size_t batch, cudaStream_t stream);
+
 }  // namespace ldpc

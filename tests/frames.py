@@ -67,3 +67,32 @@ def soft_frames(oracle, code, batch, ebn0_db, seed):
                          7.875, -7.875, 31.5 / 4, 1e-40], dtype=np.float32)
     flat[idx] = specials[rng.integers(0, specials.size, idx.size)]
     return cw, llr
+
+
+def philox4x32_10(ctr, key):
+    """Vectorised Philox4x32-10 (Salmon et al., SC'11): ctr [..., 4] and key [..., 2] uint32 -> [..., 4] uint32.
+    Test-side restatement of the generator in csrc/channel.cu; pinned by the Random123 known answers in
+    tests/test_capi_host.py."""
+    c = [np.asarray(ctr[..., i], dtype=np.uint64) for i in range(4)]
+    k = [np.asarray(key[..., i], dtype=np.uint64) for i in range(2)]
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k[0], p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ k[1], p0 & m32]
+        k = [(k[0] + np.uint64(0x9E3779B9)) & m32, (k[1] + np.uint64(0xBB67AE85)) & m32]
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_words(seed, frames, words, stream):
+    """Philox output for counters (frame, j, stream), j < words: uint32 [len(frames), words, 4]."""
+    frames = np.asarray(frames, dtype=np.uint64)
+    ctr = np.zeros((len(frames), words, 4), dtype=np.uint32)
+    ctr[..., 0] = (frames & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
+    ctr[..., 1] = (frames >> np.uint64(32)).astype(np.uint32)[:, None]
+    ctr[..., 2] = np.arange(words, dtype=np.uint32)[None, :]
+    ctr[..., 3] = stream
+    key = np.zeros((len(frames), words, 2), dtype=np.uint32)
+    key[..., 0] = seed & 0xFFFFFFFF
+    key[..., 1] = (seed >> 32) & 0xFFFFFFFF
+    return philox4x32_10(ctr, key)

@@ -142,6 +142,35 @@ def test_argument_validation_needs_no_gpu(ldpc):
     assert L.labrador_ldpc_quantise_batch_async(0, 3, p, 4.0, 31, p, 1, None) == -5
 
 
+def test_philox_restatement_known_answers():
+    """Random123 known-answer vectors for philox4x32-10; pins tests/frames.py::philox4x32_10, against which the
+    device generator (csrc/channel.cu) is compared bit for bit in tests/test_gpu_channel.py."""
+    from frames import philox4x32_10
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = philox4x32_10(np.array([ctr], dtype=np.uint32), np.array([key], dtype=np.uint32))[0]
+        assert tuple(int(x) for x in got) == want
+
+
+def test_harness_kernel_argument_validation(ldpc):
+    L = ldpc.lib
+    buf = np.zeros(64, np.uint8)
+    p = buf.ctypes.data
+    assert L.labrador_ldpc_random_data_batch(9, 1, 0, p, 1) == -1
+    assert L.labrador_ldpc_random_data_batch(0, 1, 0, None, 1) == -2
+    assert L.labrador_ldpc_random_data_batch(0, 1, 0, None, 0) == 0
+    assert L.labrador_ldpc_awgn_batch(0, 2, p, 1.0, 1.0, 31, 1, 0, p, 1) == -5          # i32 output
+    assert L.labrador_ldpc_awgn_batch(0, 0, p, 1.0, 1.0, 0, 1, 0, p, 1) == -5           # limit
+    assert L.labrador_ldpc_awgn_batch(0, 3, p, -1.0, 1.0, 0, 1, 0, p, 1) == -5          # sigma < 0
+    assert L.labrador_ldpc_awgn_batch(0, 3, p, float("nan"), 1.0, 0, 1, 0, p, 1) == -5
+    assert L.labrador_ldpc_awgn_batch(0, 3, None, 1.0, 1.0, 0, 1, 0, p, 1) == -2
+    assert L.labrador_ldpc_count_errors_batch(0, p, p, None, 1) == -2
+    assert L.labrador_ldpc_count_errors_batch(12, p, p, p, 1) == -1
+
+
 def test_python_mirror_length_asserts(ldpc):
     # the reference asserts every buffer length (src/decoder.rs:356-359, src/encoder.rs:296,312-313)
     c = ldpc.LDPCCode.TC128
