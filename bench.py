@@ -87,23 +87,23 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows), "reasons": reasons}
 
 
-def generate_shard(L, torch, frames, seed):
-    """random data -> encode (GPU encoder) -> BPSK -> AWGN -> i8 LLRs, all on the device."""
+def generate_shard(L, torch, frames, seed, first_frame):
+    """random data -> encode -> BPSK + AWGN -> i8 LLRs with this library's own kernels (csrc/channel.cu,
+    csrc/encode.cu).  The generator is counter-based (Philox keyed by `seed`, counter = frame index), so rank r
+    producing frames [r * frames, (r + 1) * frames) yields its slice of one logical run, whatever the world size.
+    LLR = 2 y / sigma^2, quantised as clamp(round(4 LLR), -31, 31)."""
     c = L.LDPCCode(CODE)
     llrs = torch.empty((frames, N), dtype=torch.int8, device="cuda")
-    g = torch.Generator(device="cuda")
-    g.manual_seed(seed)
     sigma2 = 1.0 / (2.0 * (K_INFO / N) * 10.0 ** (EBN0_DB / 10.0))
-    shifts = torch.arange(7, -1, -1, device="cuda", dtype=torch.uint8)
-    chunk = 32768
+    chunk = 65536
+    data = torch.empty((chunk, K_INFO // 8), dtype=torch.uint8, device="cuda")
+    cw = torch.empty((chunk, N // 8), dtype=torch.uint8, device="cuda")
     for f0 in range(0, frames, chunk):
         nf = min(chunk, frames - f0)
-        data = torch.randint(0, 256, (nf, K_INFO // 8), dtype=torch.uint8, device="cuda", generator=g)
-        cw = c.copy_encode_batch(data)
-        bits = ((cw.unsqueeze(-1) >> shifts) & 1).reshape(nf, N)
-        y = (1.0 - 2.0 * bits.float()) + (sigma2 ** 0.5) * torch.randn((nf, N), device="cuda", generator=g)
-        llrs[f0:f0 + nf] = torch.clamp(torch.round(4.0 * (2.0 / sigma2) * y), -31, 31).to(torch.int8)
-        del data, cw, bits, y
+        c.random_data_batch(seed, first_frame + f0, data[:nf])
+        c.copy_encode_batch(data[:nf], cw[:nf])
+        c.awgn_batch(cw[:nf], sigma2 ** 0.5, 4.0 * 2.0 / sigma2, seed, first_frame + f0, "i8", limit=31, out=llrs[f0:f0 + nf])
+    torch.cuda.synchronize()
     return llrs
 
 
@@ -210,7 +210,7 @@ def main():
     c = L.LDPCCode(CODE)
     frames = args.frames_per_gpu
 
-    llrs = generate_shard(L, torch, frames, seed=1000 + rank)
+    llrs = generate_shard(L, torch, frames, seed=1, first_frame=rank * frames)
     out = torch.empty((frames, OUT_LEN), dtype=torch.uint8, device="cuda")
     ok = torch.empty((frames,), dtype=torch.uint8, device="cuda")
     iters = torch.empty((frames,), dtype=torch.int32, device="cuda")
@@ -290,6 +290,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    llr_sum = int(llrs.view(torch.int32).sum(dtype=torch.int64).item())
     peak, peak_src = read_peaks()
     kernel_ms = ms_per_step                                 # one decode kernel per step (plus an 8-byte memset)
     achieved = ALG_BYTES_PER_FRAME * frames / (kernel_ms * 1e-3) / 1e9
@@ -302,6 +303,7 @@ def main():
                    "llr_bytes_per_gpu": frames * N, "l2": "inputs (%.1f GiB per step) far exceed the 126 MB L2" % (frames * N / 2 ** 30),
                    "kernel": c.decode_ms_kernel_name("i8"), "sharding": "independent codewords per rank, no collective"},
         "fer": fer, "mean_iters": mean_iters,
+        "llr_checksum": {"rank0_sum_of_int32_words": llr_sum, "generator": "philox4x32-10 seed 1, frames rank*frames_per_gpu.. (csrc/channel.cu)"},
         "e2e": {"value": e2e_gbit, "unit": "Gbit/s", "frames_per_gpu": ef, "h2d_bytes_per_step": ef * N,
                 "d2h_bytes_per_step": ef * (OUT_LEN + 1 + 4), "seconds_per_step": e2e_s,
                 "matches_device_resident_run": e2e_match,

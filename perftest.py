@@ -4,8 +4,8 @@
 The reference runs, per SNR point, one endless `ms_trial` loop per CPU core: random data -> encode ->
 hard_to_llrs (+-1) -> add Gaussian noise -> decode_ms::<f32>(..., 100) -> count data-bit errors, until
 more than 50 M information bits or 5000 bit errors have been seen (main.rs:46-55), then prints
-`code,snr,trials,bits,errors,BER` (main.rs:62).  Here every stage runs on the GPU in batches:
-torch generates the random data and the noise (plumbing), this library encodes, converts and decodes.
+`code,snr,trials,bits,errors,BER` (main.rs:62).  Here every stage runs on the GPU in batches and
+is a kernel of this library: counter-based random data and AWGN (csrc/channel.cu), encoder, decoder, error count.
 
     python perftest.py [--code TC512] [--snrs 0.8,0.9,...] [--llr f32] [--batch 65536] [--channel reference|ebn0]
 
@@ -21,15 +21,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-
-
-def popcount_bytes(torch, x):
-    """Number of set bits in a uint8 tensor."""
-    x = x.to(torch.int32)
-    x = x - ((x >> 1) & 0x55)
-    x = (x & 0x33) + ((x >> 2) & 0x33)
-    x = (x + (x >> 4)) & 0x0F
-    return int(x.sum().item())
 
 
 def main():
@@ -51,38 +42,36 @@ def main():
         raise SystemExit("perftest.py needs a CUDA device")
     c = L.LDPCCode[args.code]
     n, k = c.n(), c.k()
-    g = torch.Generator(device="cuda")
-    g.manual_seed(args.seed)
-    shifts = torch.arange(7, -1, -1, device="cuda", dtype=torch.uint8)
+    kb = k // 8
+    data = torch.empty((args.batch, kb), dtype=torch.uint8, device="cuda")
+    cw = torch.empty((args.batch, n // 8), dtype=torch.uint8, device="cuda")
     t_start = time.time()
     for snr in [float(s) for s in args.snrs.split(",")]:
         trials = errors = frame_errors = 0
         iters_sum = 0
+        if args.channel == "reference":                    # main.rs:15: +-1 plus N(0, (10^(-snr/10))^2), no rate term
+            sigma, llr_scale = 1.0 / 10.0 ** (snr / 10.0), 1.0
+            scale_i8, scale_i16 = 16.0, 2048.0
+        else:                                              # true Eb/N0, LLR = 2 y / sigma^2
+            sigma2 = 1.0 / (2.0 * (k / n) * 10.0 ** (snr / 10.0))
+            sigma, llr_scale = sigma2 ** 0.5, 2.0 / sigma2
+            scale_i8, scale_i16 = 4.0, 256.0
         while trials * k <= args.max_bits and errors <= args.max_errors:
-            data = torch.randint(0, 256, (args.batch, k // 8), dtype=torch.uint8, device="cuda", generator=g)
-            cw = c.copy_encode_batch(data)                                   # main.rs:10-12
-            if args.channel == "reference":
-                llr = c.hard_to_llrs_batch(cw, "f32")                        # main.rs:13-14
-                llr += torch.randn((args.batch, n), device="cuda", generator=g) * (1.0 / 10.0 ** (snr / 10.0))  # :15-18
-                scale_i8, scale_i16 = 16.0, 2048.0
-            else:
-                bits = ((cw.unsqueeze(-1) >> shifts) & 1).reshape(args.batch, n)
-                sigma2 = 1.0 / (2.0 * (k / n) * 10.0 ** (snr / 10.0))
-                y = (1.0 - 2.0 * bits.float()) + (sigma2 ** 0.5) * torch.randn((args.batch, n), device="cuda", generator=g)
-                llr = (2.0 / sigma2) * y
-                scale_i8, scale_i16 = 4.0, 256.0
-            if args.llr == "i8":
-                q = torch.clamp(torch.round(scale_i8 * llr), -31, 31).to(torch.int8)
+            # every stage below is a kernel of this library; frames are numbered across the whole run
+            c.random_data_batch(args.seed, trials, data)                                   # main.rs:10
+            c.copy_encode_batch(data, cw)                                                  # main.rs:11-12
+            if args.llr == "i8":                                                           # main.rs:13-18
+                q = c.awgn_batch(cw, sigma, llr_scale * scale_i8, args.seed, trials, "i8", limit=31)
             elif args.llr == "i16":
-                q = torch.clamp(torch.round(scale_i16 * llr), -8191, 8191).to(torch.int16)
-            elif args.llr == "f64":
-                q = llr.double()
+                q = c.awgn_batch(cw, sigma, llr_scale * scale_i16, args.seed, trials, "i16", limit=8191)
             else:
-                q = llr
-            out, ok, iters = c.decode_ms_batch(q.contiguous(), args.max_iters)   # main.rs:19-22
-            diff = out[:, : k // 8] ^ data                                   # main.rs:23-28
-            errors += popcount_bytes(torch, diff)
-            frame_errors += int((diff != 0).any(dim=1).sum().item())
+                q = c.awgn_batch(cw, sigma, llr_scale, args.seed, trials, "f32")
+                if args.llr == "f64":
+                    q = q.double()
+            out, ok, iters = c.decode_ms_batch(q, args.max_iters)                          # main.rs:19-22
+            errs = c.count_errors_batch(out, data)                                         # main.rs:23-28
+            errors += int(errs.sum().item())
+            frame_errors += int((errs != 0).sum().item())
             iters_sum += int(iters.sum().item())
             trials += args.batch
         bits_total = trials * k
