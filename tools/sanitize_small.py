@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.
 import numpy as np
 import labrador_ldpc_b200 as L
 import pyoracle
-from frames import make_frames, hard_frames
+from frames import make_frames, hard_frames, soft_frames, quantise_soft
 o = pyoracle.Oracle()
 for code, ty, eb in ((8, "i8", 2.0), (5, "i8", 2.0), (6, "i8", 4.0), (5, "f32", 2.0), (3, "i8", 4.0), (0, "i8", 3.0), (2, "f32", 3.0)):
     c = L.LDPCCode(code)
@@ -13,11 +13,27 @@ for code, ty, eb in ((8, "i8", 2.0), (5, "i8", 2.0), (6, "i8", 4.0), (5, "f32", 
     want = o.decode_ms_batch(code, llrs, 30, nthreads=4)
     got = c.decode_ms_batch(llrs, 30)
     assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want)), (code, ty)
-for code in (0, 5, 8):
+for code in (0, 1, 2, 3, 5, 6, 8):
     c = L.LDPCCode(code)
     d, cw, rx = hard_frames(o, code, 16, 3, seed=2)
     got = c.decode_bf_batch(rx, 20); want = o.decode_bf_batch(code, rx, 20)
     assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want)), code
     assert np.array_equal(c.copy_encode_batch(d), cw)
     l = c.hard_to_llrs_batch(cw, "f32"); assert np.array_equal(c.llrs_to_hard_batch(l), cw)
+same = lambda got, want: all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want))
+for code, eb in ((0, 3.0), (3, 3.6), (5, 2.0), (8, 2.0)):                       # fused front ends
+    c = L.LDPCCode(code)
+    _, soft = soft_frames(o, code, 16, eb, seed=3)
+    assert same(c.decode_ms_soft_batch(soft, 4.0, 31, 30, "i8"), o.decode_ms_batch(code, quantise_soft(soft, 4.0, 31, np.int8), 30, nthreads=4))
+    assert same(c.decode_ms_soft_batch(soft, 256.0, 8191, 30, "i16"), o.decode_ms_batch(code, quantise_soft(soft, 256.0, 8191, np.int16), 30, nthreads=4))
+    _, _, rx = hard_frames(o, code, 9, 2, seed=4)
+    assert same(c.decode_ms_hard_batch(rx, 30), o.decode_ms_batch(code, np.stack([o.hard_to_llrs(code, r, "i8") for r in rx]), 30, nthreads=4))
+for code in (0, 5):                                                              # harness kernels
+    c = L.LDPCCode(code)
+    data = c.random_data_batch(5, 0, np.zeros((13, c.k() // 8), np.uint8))
+    cw = c.copy_encode_batch(data)
+    for ty, lim in (("f32", 0), ("i8", 31), ("i16", 8191)):
+        c.awgn_batch(cw, 0.7, 9.0, 5, 0, ty, limit=lim)
+    out = np.zeros((13, c.output_len()), np.uint8); out[:, : c.n() // 8] = cw
+    assert not c.count_errors_batch(out, data).any()
 print("sanitize_small OK")
