@@ -141,7 +141,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                         par_any |= par != 0;
                         suf[7] = a[7];
 #pragma unroll
-                        for (int k = 6; k >= 1; k--) suf[k] = a[k] < suf[k + 1] ? a[k] : suf[k + 1];
+                        for (int k = 6; k >= 1; k--) suf[k] = A::min(a[k], suf[k + 1]);
                         CT pre = a[0];
                         tc_static_for<0, 8>([&](auto ki) {
                             constexpr int k = decltype(ki)::value;
@@ -149,8 +149,8 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                             CT mu;
                             if constexpr (k == 0) mu = suf[1];
                             else if constexpr (k == 7) mu = pre;
-                            else mu = pre < suf[k + 1] ? pre : suf[k + 1];
-                            if constexpr (k > 0 && k < 7) pre = pre < a[k] ? pre : a[k];
+                            else mu = A::min(pre, suf[k + 1]);
+                            if constexpr (k > 0 && k < 7) pre = A::min(pre, a[k]);
                             if (stot != sg[k]) mu = A::neg(mu);                           // :398-405
                             msg[b * M + i] = (ST)mu;
                         });

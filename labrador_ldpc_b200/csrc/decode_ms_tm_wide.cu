@@ -182,7 +182,7 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                     // min over the other edges = (|v| == min1 ? min2 : min1)  (:391-395)
                     suf[DC - 1] = a[DC - 1];
 #pragma unroll
-                    for (int k = DC - 2; k >= 1; k--) suf[k] = a[k] < suf[k + 1] ? a[k] : suf[k + 1];
+                    for (int k = DC - 2; k >= 1; k--) suf[k] = A::min(a[k], suf[k + 1]);
                     CT pre = a[0];
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
@@ -191,8 +191,8 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                             CT mu;
                             if constexpr (k == 0) mu = suf[1];
                             else if constexpr (k == DC - 1) mu = pre;
-                            else mu = pre < suf[k + 1] ? pre : suf[k + 1];
-                            if constexpr (k > 0 && k < DC - 1) pre = pre < a[k] ? pre : a[k];
+                            else mu = A::min(pre, suf[k + 1]);
+                            if constexpr (k > 0 && k < DC - 1) pre = A::min(pre, a[k]);
                             CT u = mu;
                             if (stot != sg[k]) u = A::neg(u);                          // :398-405
                             if constexpr (P::blk(b).isp) msg[count_p<P>(b) * M + e] = (ST)u;

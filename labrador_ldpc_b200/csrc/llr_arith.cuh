@@ -29,6 +29,7 @@ template <> struct Arith<int8_t> {
     __device__ static __forceinline__ int sat_add(int a, int b) { return max(__viaddmin_s32(a, b, 127), -128); }
     __device__ static __forceinline__ int sat_sub(int a, int b) { return max(__viaddmin_s32(a, -b, 127), -128); }
     __device__ static __forceinline__ int neg(int x) { return -x; }
+    __device__ static __forceinline__ int min(int a, int b) { return a < b ? a : b; }
     __device__ static __forceinline__ bool hard_bit(int x) { return x < 0; }
 };
 
@@ -42,6 +43,7 @@ template <> struct Arith<int16_t> {
     __device__ static __forceinline__ int sat_add(int a, int b) { return max(__viaddmin_s32(a, b, 32767), -32768); }
     __device__ static __forceinline__ int sat_sub(int a, int b) { return max(__viaddmin_s32(a, -b, 32767), -32768); }
     __device__ static __forceinline__ int neg(int x) { return -x; }
+    __device__ static __forceinline__ int min(int a, int b) { return a < b ? a : b; }
     __device__ static __forceinline__ bool hard_bit(int x) { return x < 0; }
 };
 
@@ -58,6 +60,7 @@ template <> struct Arith<int32_t> {
     __device__ static __forceinline__ int32_t sat_add(int32_t a, int32_t b) { return clamp64((long long)a + (long long)b); }
     __device__ static __forceinline__ int32_t sat_sub(int32_t a, int32_t b) { return clamp64((long long)a - (long long)b); }
     __device__ static __forceinline__ int32_t neg(int32_t x) { return -x; }
+    __device__ static __forceinline__ int32_t min(int32_t a, int32_t b) { return a < b ? a : b; }
     __device__ static __forceinline__ bool hard_bit(int32_t x) { return x < 0; }
 };
 
@@ -67,7 +70,10 @@ template <> struct Arith<float> {
     __device__ static __forceinline__ float zero() { return 0.0f; }
     __device__ static __forceinline__ float one() { return 1.0f; }
     __device__ static __forceinline__ float maxval() { return FLT_MAX; }
-    __device__ static __forceinline__ float abs(float x) { return __uint_as_float(__float_as_uint(x) & 0x7FFFFFFFu); }
+    // fabsf clears the sign bit exactly like the reference's mask (:60-63) and folds into an operand modifier
+    __device__ static __forceinline__ float abs(float x) { return fabsf(x); }
+    // a < b ? a : b for the minima over |v| (never NaN, never -0): one FMNMX instead of FSETP + FSEL
+    __device__ static __forceinline__ float min(float a, float b) { return fminf(a, b); }
     __device__ static __forceinline__ float sat_add(float a, float b) { return __fadd_rn(a, b); }
     __device__ static __forceinline__ float sat_sub(float a, float b) { return __fsub_rn(a, b); }
     __device__ static __forceinline__ float neg(float x) { return -x; }
@@ -80,9 +86,8 @@ template <> struct Arith<double> {
     __device__ static __forceinline__ double zero() { return 0.0; }
     __device__ static __forceinline__ double one() { return 1.0; }
     __device__ static __forceinline__ double maxval() { return DBL_MAX; }
-    __device__ static __forceinline__ double abs(double x) {
-        return __longlong_as_double(__double_as_longlong(x) & 0x7FFFFFFFFFFFFFFFll);
-    }
+    __device__ static __forceinline__ double abs(double x) { return fabs(x); }
+    __device__ static __forceinline__ double min(double a, double b) { return fmin(a, b); }
     __device__ static __forceinline__ double sat_add(double a, double b) { return __dadd_rn(a, b); }
     __device__ static __forceinline__ double sat_sub(double a, double b) { return __dsub_rn(a, b); }
     __device__ static __forceinline__ double neg(double x) { return -x; }
