@@ -582,7 +582,7 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
 
 // Variant selection.  Several arithmetic variants are compiled per code; the default per code is the one that
 // measured fastest on B200 (profiles/r01_tm_variants.md).  LABRADOR_LDPC_TM_ARITH=1|2|3|4|5 overrides (A/B runs);
-// 52 / 53 (TM5120 only) = ARITH 5 compiled for 2 / 3 resident CTAs per SM (128 / 80 registers, a few spills).
+// 52 (TM5120 only) = ARITH 5 compiled for 2 resident CTAs per SM (128 registers, 15 spilled words).
 template <int RATE, int M>
 cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const void *l, uint8_t *output,
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
@@ -594,8 +594,6 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
             if (arith == 3) return launch_tm<RATE, M, 2, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 5) return launch_tm<RATE, M, 2, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 4) return launch_tm<RATE, M, 2, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-            if (arith == 46) return launch_tm<RATE, M, 2, 4, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-            if (arith == 42) return launch_tm<RATE, M, 2, 4, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             return launch_tm<RATE, M, 2, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         }
     }
@@ -604,10 +602,8 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 5) return launch_tm<RATE, M, 1, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
         if (arith == 52) return launch_tm<RATE, M, 1, 5, 0, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-        if (arith == 53) return launch_tm<RATE, M, 1, 5, 0, 3>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     }
     if (arith == 4) return launch_tm<RATE, M, 1, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-    if (arith == 46) return launch_tm<RATE, M, 1, 4, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     return launch_tm<RATE, M, 1, 2, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
 }
 
