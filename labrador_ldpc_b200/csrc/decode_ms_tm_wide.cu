@@ -26,6 +26,47 @@ namespace {
 
 constexpr int kMaxDegW = 18;
 
+// all four bytes <- the most significant bit of byte BYTE of x (0xFFFFFFFF or 0)
+template <int BYTE> __device__ __forceinline__ uint32_t sign_mask_of_byte(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(x), "n"(0x1111 * (8 + BYTE)));
+    return r;
+}
+
+// u_k = min over the other edges of one check, three-input minima at pair boundaries (see decode_ms_tm.cu)
+template <int DC>
+__device__ __forceinline__ void min_excluding_self_u32(const uint32_t (&a)[kMaxDegW], uint32_t (&mu)[kMaxDegW]) {
+    constexpr int NPAIR = DC / 2;
+    constexpr bool ODD = (DC & 1) != 0;
+    uint32_t suf[kMaxDegW / 2 + 2];
+    if constexpr (ODD) suf[NPAIR] = a[DC - 1];
+#pragma unroll
+    for (int j = NPAIR - 1; j >= 1; j--) {
+        if (j == NPAIR - 1 && !ODD) suf[j] = min(a[2 * j], a[2 * j + 1]);
+        else suf[j] = __vimin3_u32(a[2 * j], a[2 * j + 1], suf[j + 1]);
+    }
+    uint32_t pre = 0;
+#pragma unroll
+    for (int j = 0; j < NPAIR; j++) {
+        const bool has_pre = j > 0, has_suf = (j + 1 < NPAIR) || ODD;
+        if (has_pre && has_suf) {
+            mu[2 * j] = __vimin3_u32(pre, a[2 * j + 1], suf[j + 1]);
+            mu[2 * j + 1] = __vimin3_u32(pre, a[2 * j], suf[j + 1]);
+        } else if (has_suf) {
+            mu[2 * j] = min(a[2 * j + 1], suf[j + 1]);
+            mu[2 * j + 1] = min(a[2 * j], suf[j + 1]);
+        } else if (has_pre) {
+            mu[2 * j] = min(pre, a[2 * j + 1]);
+            mu[2 * j + 1] = min(pre, a[2 * j]);
+        } else {
+            mu[2 * j] = a[2 * j + 1];
+            mu[2 * j + 1] = a[2 * j];
+        }
+        if (j + 1 < NPAIR || ODD) pre = has_pre ? __vimin3_u32(pre, a[2 * j], a[2 * j + 1]) : min(a[2 * j], a[2 * j + 1]);
+    }
+    if constexpr (ODD) mu[DC - 1] = pre;
+}
+
 template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(NT)
 decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
@@ -43,6 +84,12 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
     constexpr int NV = NCOL * M, N = (NCOL - 1) * M, NC = NROW * M;
     constexpr int HBW = NV / 32, SYW = NC / 32;
     constexpr int CA = P::blk(0).col, CP = NCOL - 1;      // the two columns row 0 touches (see decode_ms_tm.cu)
+    // i8 / i16: the biased representation of the packed i8 kernel (decode_ms_tm.cu), one value per 32-bit register:
+    //   marginal VA = va + B in [0, 2B-1], saturating_add = one VIADDMNMX.RELU;  message C = MAXV - clamp(va - u, +-MAXV);
+    //   check side: sign = bit BITS-1 of C, |v| = |C - MAXV|, kill = that bit of (C ^ old) & (C ^ (old + 1)).
+    constexpr bool kBiased = std::is_same<T, int8_t>::value || std::is_same<T, int16_t>::value;
+    constexpr int BITS = 8 * (int)sizeof(T);
+    constexpr int kB = kBiased ? (1 << (BITS - 1)) : 0, kMaxV = kB - 1;
     static_assert(M % NT == 0 && NT % 32 == 0 && Q % 32 == 0, "whole warps per quarter");
     static_assert(SYW <= NT && NCOL - 2 <= 16, "one thread per syndrome word; packed hard bits fit");
 
@@ -84,11 +131,14 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
         for (int ei = 0; ei < EPT; ei++) {
             const int e = tid + ei * NT;
 #pragma unroll
-            for (int c = 0; c < NCOL; c++) Lv[c][ei] = c < NCOL - 1 ? front_load<FRONT, T>(llr, c * M + e, fscale, flimit) : A::zero();   // :382-383
+            for (int c = 0; c < NCOL; c++) {
+                Lv[c][ei] = c < NCOL - 1 ? front_load<FRONT, T>(llr, c * M + e, fscale, flimit) : A::zero();   // :382-383
+                if constexpr (kBiased) Lv[c][ei] += (CT)kB;
+            }
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][ei] = A::zero();
 #pragma unroll
-            for (int b = 0; b < NB; b++) vold[b][ei] = A::zero();
+            for (int b = 0; b < NB; b++) vold[b][ei] = kBiased ? (CT)kMaxV : A::zero();
 #pragma unroll
             for (int p = 0; p < NP; p++) msg[p * M + e] = (ST)A::zero();
         }
@@ -130,10 +180,14 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                             if constexpr (P::blk(b).isp) u = (CT)msg[paddr[count_p<P>(b)][ei]];
                             else u = idm[count_i<P>(b)][ei];
                             ub[k] = u;
-                            va = A::sat_add(va, u);                                   // :408, ascending idx
+                            if constexpr (kBiased) va = (CT)__viaddmin_s32_relu((int)va, (int)u, 2 * kB - 1);
+                            else va = A::sat_add(va, u);                              // :408, ascending idx
                         }
                     });
-                    const bool hard = A::hard_bit(va);
+                    bool hard;
+                    if constexpr (kBiased) hard = (int)va < kB;
+                    else hard = A::hard_bit(va);
+                    [[maybe_unused]] const int van = kBiased ? (2 * kB - 1) - (int)va : 0;
                     if constexpr (c == CA || c == CP) {
                         const unsigned bw = __ballot_sync(0xFFFFFFFFu, hard);
                         if (lane == 0) hb[(c * M + tid + ei * NT) >> 5] = bw;
@@ -144,7 +198,9 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).col == c) {
                             constexpr int k = pos_in_col<P>(b);
-                            const CT nv = A::sat_sub(va, ub[k]);                      // :421
+                            CT nv;
+                            if constexpr (kBiased) nv = (CT)__viaddmin_s32_relu(van, (int)ub[k], 2 * kMaxV);
+                            else nv = A::sat_sub(va, ub[k]);                          // :421
                             if constexpr (P::blk(b).isp) msg[paddr[count_p<P>(b)][ei]] = (ST)nv;
                             else idm[count_i<P>(b)][ei] = nv;
                         }
@@ -160,6 +216,38 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                 static_for<0, NROW>([&](auto ri) {
                     constexpr int r = decltype(ri)::value;
                     constexpr int DC = row_degree<P>(r);
+                    if constexpr (kBiased) {
+                        uint32_t a[kMaxDegW], ck[kMaxDegW], mu[kMaxDegW];
+                        uint32_t sx = 0;
+                        static_for<0, NB>([&](auto bi) {
+                            constexpr int b = decltype(bi)::value;
+                            if constexpr (P::blk(b).row == r) {
+                                constexpr int k = pos_in_row<P>(b);
+                                uint32_t cv;
+                                if constexpr (P::blk(b).isp) cv = (uint32_t)msg[count_p<P>(b) * M + e];
+                                else cv = (uint32_t)idm[count_i<P>(b)][ei];
+                                const uint32_t old = (uint32_t)vold[b][ei];
+                                const uint32_t x = (cv ^ old) & (cv ^ (old + 1u));       // bit BITS-1: sign flipped and old != 0
+                                const uint32_t km = sign_mask_of_byte<BITS / 8 - 1>(x);
+                                const uint32_t cor = (cv & ~km) | ((uint32_t)kMaxV & km);   // killed -> v = 0  (:422-426)
+                                vold[b][ei] = (CT)cor;
+                                ck[k] = cor;
+                                a[k] = __usad(cor, (uint32_t)kMaxV, 0u);                 // |v|
+                                sx ^= cor;                                               // bit BITS-1: product of signs
+                            }
+                        });
+                        min_excluding_self_u32<DC>(a, mu);                               // :391-395
+                        static_for<0, NB>([&](auto bi) {
+                            constexpr int b = decltype(bi)::value;
+                            if constexpr (P::blk(b).row == r) {
+                                constexpr int k = pos_in_row<P>(b);
+                                const uint32_t nm = sign_mask_of_byte<BITS / 8 - 1>(sx ^ ck[k]);   // u negative  (:398-405)
+                                const uint32_t u = (mu[k] + nm) ^ nm;                    // +-mu, two's complement
+                                if constexpr (P::blk(b).isp) msg[count_p<P>(b) * M + e] = (ST)u;
+                                else idm[count_i<P>(b)][ei] = (CT)u;
+                            }
+                        });
+                    } else {
                     CT a[kMaxDegW], suf[kMaxDegW];
                     bool sg[kMaxDegW];
                     bool stot = false;
@@ -199,6 +287,7 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                             else idm[count_i<P>(b)][ei] = u;
                         }
                     });
+                    }
                 });
             }
             // ---- parity of the marginals' hard bits (:445-453): two-stage, bit-packed ----
