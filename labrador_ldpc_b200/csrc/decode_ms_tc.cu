@@ -18,6 +18,7 @@
 
 #include <type_traits>
 
+#include "biased_arith.cuh"
 #include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
@@ -45,6 +46,10 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
     constexpr int CWW = 32 / G;                      // codewords per warp
     constexpr int N = 8 * M, NC = 4 * M, E = 32 * M;
     constexpr unsigned kFull = 0xFFFFFFFFu;
+    // i8 / i16 run in the biased representation of biased_arith.cuh
+    constexpr bool kBiased = std::is_same<T, int8_t>::value || std::is_same<T, int16_t>::value;
+    constexpr int BITS = 8 * (int)sizeof(T);
+    constexpr int kB = kBiased ? (1 << (BITS - 1)) : 0, kMaxV = kB - 1;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,9 +76,12 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
         for (int ei = 0; ei < EPT; ei++) {
             const int e = sl + ei * G;
 #pragma unroll
-            for (int c = 0; c < 8; c++) Lv[c][ei] = front_load<FRONT, T>(llr, c * M + e, fscale, flimit);
+            for (int c = 0; c < 8; c++) {
+                Lv[c][ei] = front_load<FRONT, T>(llr, c * M + e, fscale, flimit);
+                if constexpr (kBiased) Lv[c][ei] += (CT)kB;
+            }
 #pragma unroll
-            for (int b = 0; b < 32; b++) { vold[b][ei] = A::zero(); msg[b * M + e] = (ST)A::zero(); }
+            for (int b = 0; b < 32; b++) { vold[b][ei] = kBiased ? (CT)kMaxV : A::zero(); msg[b * M + e] = (ST)A::zero(); }
 #pragma unroll
             for (int c = 0; c < 8; c++) hbv[c * M + e] = 0;
         }
@@ -98,15 +106,21 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                                 const int i = (j - (int)prm.shift[b]) & (M - 1);
                                 const CT u = (CT)msg[b * M + i];
                                 ub[tc_pos_in_col(b)] = u;
-                                va = A::sat_add(va, u);                                  // :408
+                                if constexpr (kBiased) va = (CT)__viaddmin_s32_relu((int)va, (int)u, 2 * kB - 1);
+                                else va = A::sat_add(va, u);                             // :408
                             }
                         });
-                        hbv[c * M + j] = A::hard_bit(va) ? 1 : 0;
+                        if constexpr (kBiased) hbv[c * M + j] = (int)va < kB ? 1 : 0;
+                        else hbv[c * M + j] = A::hard_bit(va) ? 1 : 0;
+                        [[maybe_unused]] const int van = kBiased ? (2 * kB - 1) - (int)va : 0;
                         tc_static_for<0, 32>([&](auto bi) {
                             constexpr int b = decltype(bi)::value;
                             if constexpr (tc_blk(b).col == c) {
                                 const int i = (j - (int)prm.shift[b]) & (M - 1);
-                                msg[b * M + i] = (ST)A::sat_sub(va, ub[tc_pos_in_col(b)]);   // :421
+                                if constexpr (kBiased)
+                                    msg[b * M + i] = (ST)__viaddmin_s32_relu(van, (int)ub[tc_pos_in_col(b)], 2 * kMaxV);
+                                else
+                                    msg[b * M + i] = (ST)A::sat_sub(va, ub[tc_pos_in_col(b)]);   // :421
                             }
                         });
                     });
@@ -121,6 +135,33 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                     const int i = sl + ei * G;
                     tc_static_for<0, 4>([&](auto ri) {
                         constexpr int r = decltype(ri)::value;
+                        if constexpr (kBiased) {
+                            uint32_t a[8], ck[8], mu[8];
+                            uint32_t sx = 0;
+                            int par = 0;
+                            tc_static_for<0, 8>([&](auto ki) {
+                                constexpr int k = decltype(ki)::value;
+                                constexpr int b = r * 8 + k;
+                                const uint32_t cv = (uint32_t)msg[b * M + i];
+                                const uint32_t old = (uint32_t)vold[b][ei];
+                                const uint32_t x = (cv ^ old) & (cv ^ (old + 1u));       // bit BITS-1: sign flipped and old != 0
+                                const uint32_t km = sign_mask_of_byte<BITS / 8 - 1>(x);
+                                const uint32_t cor = (cv & ~km) | ((uint32_t)kMaxV & km);   // killed -> v = 0  (:422-426)
+                                vold[b][ei] = (CT)cor;
+                                ck[k] = cor;
+                                a[k] = __usad(cor, (uint32_t)kMaxV, 0u);                 // |v|
+                                sx ^= cor;
+                                par ^= hbv[tc_blk(b).col * M + ((i + (int)prm.shift[b]) & (M - 1))];   // :445-447
+                            });
+                            par_any |= par != 0;
+                            min_excluding_self_u32<8, 8>(a, mu);                         // :391-395
+                            tc_static_for<0, 8>([&](auto ki) {
+                                constexpr int k = decltype(ki)::value;
+                                constexpr int b = r * 8 + k;
+                                const uint32_t nm = sign_mask_of_byte<BITS / 8 - 1>(sx ^ ck[k]);   // :398-405
+                                msg[b * M + i] = (ST)((mu[k] + nm) ^ nm);
+                            });
+                        } else {
                         CT a[8], suf[8];
                         bool sg[8];
                         bool stot = false;
@@ -154,6 +195,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                             if (stot != sg[k]) mu = A::neg(mu);                           // :398-405
                             msg[b * M + i] = (ST)mu;
                         });
+                        }
                     });
                 }
             }

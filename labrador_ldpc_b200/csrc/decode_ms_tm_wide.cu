@@ -14,6 +14,7 @@
 
 #include <cstdlib>
 
+#include "biased_arith.cuh"
 #include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
@@ -25,47 +26,6 @@ using namespace tm;
 namespace {
 
 constexpr int kMaxDegW = 18;
-
-// all four bytes <- the most significant bit of byte BYTE of x (0xFFFFFFFF or 0)
-template <int BYTE> __device__ __forceinline__ uint32_t sign_mask_of_byte(uint32_t x) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(x), "n"(0x1111 * (8 + BYTE)));
-    return r;
-}
-
-// u_k = min over the other edges of one check, three-input minima at pair boundaries (see decode_ms_tm.cu)
-template <int DC>
-__device__ __forceinline__ void min_excluding_self_u32(const uint32_t (&a)[kMaxDegW], uint32_t (&mu)[kMaxDegW]) {
-    constexpr int NPAIR = DC / 2;
-    constexpr bool ODD = (DC & 1) != 0;
-    uint32_t suf[kMaxDegW / 2 + 2];
-    if constexpr (ODD) suf[NPAIR] = a[DC - 1];
-#pragma unroll
-    for (int j = NPAIR - 1; j >= 1; j--) {
-        if (j == NPAIR - 1 && !ODD) suf[j] = min(a[2 * j], a[2 * j + 1]);
-        else suf[j] = __vimin3_u32(a[2 * j], a[2 * j + 1], suf[j + 1]);
-    }
-    uint32_t pre = 0;
-#pragma unroll
-    for (int j = 0; j < NPAIR; j++) {
-        const bool has_pre = j > 0, has_suf = (j + 1 < NPAIR) || ODD;
-        if (has_pre && has_suf) {
-            mu[2 * j] = __vimin3_u32(pre, a[2 * j + 1], suf[j + 1]);
-            mu[2 * j + 1] = __vimin3_u32(pre, a[2 * j], suf[j + 1]);
-        } else if (has_suf) {
-            mu[2 * j] = min(a[2 * j + 1], suf[j + 1]);
-            mu[2 * j + 1] = min(a[2 * j], suf[j + 1]);
-        } else if (has_pre) {
-            mu[2 * j] = min(pre, a[2 * j + 1]);
-            mu[2 * j + 1] = min(pre, a[2 * j]);
-        } else {
-            mu[2 * j] = a[2 * j + 1];
-            mu[2 * j + 1] = a[2 * j];
-        }
-        if (j + 1 < NPAIR || ODD) pre = has_pre ? __vimin3_u32(pre, a[2 * j], a[2 * j + 1]) : min(a[2 * j], a[2 * j + 1]);
-    }
-    if constexpr (ODD) mu[DC - 1] = pre;
-}
 
 template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(NT)
@@ -236,7 +196,7 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                                 sx ^= cor;                                               // bit BITS-1: product of signs
                             }
                         });
-                        min_excluding_self_u32<DC>(a, mu);                               // :391-395
+                        min_excluding_self_u32<DC, kMaxDegW>(a, mu);                               // :391-395
                         static_for<0, NB>([&](auto bi) {
                             constexpr int b = decltype(bi)::value;
                             if constexpr (P::blk(b).row == r) {
