@@ -53,12 +53,18 @@ template <> struct Arith<int32_t> {
     __device__ static __forceinline__ int32_t zero() { return 0; }
     __device__ static __forceinline__ int32_t one() { return 1; }
     __device__ static __forceinline__ int32_t maxval() { return INT32_MAX; }
-    __device__ static __forceinline__ int32_t clamp64(long long x) {
-        return (int32_t)(x < (long long)INT32_MIN ? (long long)INT32_MIN : (x > (long long)INT32_MAX ? (long long)INT32_MAX : x));
+    // |INT32_MIN| wraps to 0x80000000, which the unsigned minimum brings back to INT32_MAX (saturating_abs)
+    __device__ static __forceinline__ int32_t abs(int32_t x) { return (int32_t)::min((uint32_t)::abs(x), (uint32_t)INT32_MAX); }
+    __device__ static __forceinline__ int32_t sat_add(int32_t a, int32_t b) {
+        int32_t r;
+        asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
     }
-    __device__ static __forceinline__ int32_t abs(int32_t x) { return x == INT32_MIN ? INT32_MAX : (x < 0 ? -x : x); }
-    __device__ static __forceinline__ int32_t sat_add(int32_t a, int32_t b) { return clamp64((long long)a + (long long)b); }
-    __device__ static __forceinline__ int32_t sat_sub(int32_t a, int32_t b) { return clamp64((long long)a - (long long)b); }
+    __device__ static __forceinline__ int32_t sat_sub(int32_t a, int32_t b) {
+        int32_t r;
+        asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+    }
     __device__ static __forceinline__ int32_t neg(int32_t x) { return -x; }
     __device__ static __forceinline__ int32_t min(int32_t a, int32_t b) { return a < b ? a : b; }
     __device__ static __forceinline__ bool hard_bit(int32_t x) { return x < 0; }

@@ -237,6 +237,21 @@ def test_decode_ms_i16_saturation_stress(ldpc, oracle, code):
     assert_exact(got, want, NAMES[code] + " i16 stress")
 
 
+@pytest.mark.parametrize("code", [1, 3, 5])
+def test_decode_ms_i32_saturation_stress(ldpc, oracle, code):
+    """Full-range i32 LLRs (incl. INT32_MIN): saturating add / sub / abs corners of the 32-bit path."""
+    c = ldpc.LDPCCode(code)
+    rng = np.random.default_rng(550 + code)
+    llrs = rng.integers(-2 ** 31, 2 ** 31, (16, c.n()), dtype=np.int64).astype(np.int32)
+    llrs[0, :] = -2 ** 31
+    llrs[1, :] = 2 ** 31 - 1
+    llrs[2, ::2] = -2 ** 31
+    for maxiters in (1, 3, 7):
+        want = oracle.decode_ms_batch(code, llrs, maxiters, nthreads=8)
+        got = c.decode_ms_batch(llrs, maxiters)
+        assert_exact(got, want, "%s i32 stress maxiters=%d" % (NAMES[code], maxiters))
+
+
 def test_decode_ms_maxiters_edge_cases(ldpc, oracle):
     for code in (0, 5):
         c = ldpc.LDPCCode(code)

@@ -18,6 +18,8 @@ def gen(code, batch, ebn0, ty="i8", seed=1):
         return data, torch.clamp(torch.round(4.0 * llr), -31, 31).to(torch.int8).contiguous()
     if ty == "i16":
         return data, torch.clamp(torch.round(256.0 * llr), -8191, 8191).to(torch.int16).contiguous()
+    if ty == "i32":
+        return data, torch.round(65536.0 * llr).to(torch.int32).contiguous()
     if ty == "f32":
         return data, llr.contiguous()
     return data, llr.double().contiguous()
