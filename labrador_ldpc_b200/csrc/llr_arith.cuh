@@ -93,7 +93,8 @@ template <> struct Arith<double> {
     __device__ static __forceinline__ double one() { return 1.0; }
     __device__ static __forceinline__ double maxval() { return DBL_MAX; }
     __device__ static __forceinline__ double abs(double x) { return fabs(x); }
-    __device__ static __forceinline__ double min(double a, double b) { return fmin(a, b); }
+    // no native f64 min/max instruction: the compare-and-select form is the shorter one
+    __device__ static __forceinline__ double min(double a, double b) { return a < b ? a : b; }
     __device__ static __forceinline__ double sat_add(double a, double b) { return __dadd_rn(a, b); }
     __device__ static __forceinline__ double sat_sub(double a, double b) { return __dsub_rn(a, b); }
     __device__ static __forceinline__ double neg(double x) { return -x; }

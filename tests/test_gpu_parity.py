@@ -425,6 +425,22 @@ def test_full_size_properties_tm8192(ldpc, oracle):
     assert_exact((out[:96].cpu().numpy(), ok[:96].cpu().numpy(), iters[:96].cpu().numpy()), want, "prefix sample")
 
 
+def test_shutdown_and_reinitialise(ldpc, oracle):
+    """labrador_ldpc_cuda_shutdown releases every device resource; the next call re-initialises transparently."""
+    c = ldpc.LDPCCode.TM2048
+    _, _, llrs = make_frames(oracle, 5, 32, 2.0, seed=5, ty="i8")
+    want = oracle.decode_ms_batch(5, llrs, 50, nthreads=8)
+    assert_exact(c.decode_ms_batch(llrs, 50), want, "before shutdown")
+    ldpc.shutdown()
+    assert ldpc.lib.labrador_ldpc_cuda_device_count() == 0
+    assert_exact(c.decode_ms_batch(llrs, 50), want, "after shutdown (lazy re-init)")
+    ldpc.shutdown()
+    ldpc.init([0])
+    assert ldpc.lib.labrador_ldpc_cuda_device_count() == 1
+    _, _, rx = hard_frames(oracle, 5, 16, 3, seed=6)
+    assert_exact(c.decode_bf_batch(rx, 20), oracle.decode_bf_batch(5, rx, 20), "bf after explicit re-init")
+
+
 def test_launch_counter_and_kernel_names(ldpc):
     before = ldpc.kernel_launch_count()
     c = ldpc.LDPCCode.TC128
