@@ -31,6 +31,9 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 
+// message slots per codeword in a warp's shared-memory slice (32 M messages + bank-skew padding)
+template <int M> __host__ __device__ constexpr int tc_msg_stride() { return M < 32 ? 32 * M + M : 32 * M; }
+
 template <int M, class T, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
@@ -55,23 +58,41 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cwl = lane / G, sl = lane % G;
     // per-warp slice: messages [CWW][32][M] of T, then hard bits [CWW][N] bytes
-    constexpr size_t kWarpBytes = sizeof(ST) * CWW * E + (size_t)CWW * N;
+    // the codewords of one warp start G message slots apart modulo 32, so that their lanes use disjoint banks
+    constexpr int ESTRIDE = tc_msg_stride<M>();
+    constexpr size_t kWarpBytes = sizeof(ST) * CWW * ESTRIDE + (size_t)CWW * N;
     unsigned char *wbase = smem_raw + (size_t)warp * ((kWarpBytes + 15) & ~(size_t)15);
-    ST *msg = reinterpret_cast<ST *>(wbase) + (size_t)cwl * E;
-    uint8_t *hbv = wbase + sizeof(ST) * CWW * E + (size_t)cwl * N;
+    ST *msg = reinterpret_cast<ST *>(wbase) + (size_t)cwl * ESTRIDE;
+    uint8_t *hbv = wbase + sizeof(ST) * CWW * ESTRIDE + (size_t)cwl * N;
     const unsigned group_mask = (G == 32 ? kFull : ((1u << G) - 1u)) << (cwl * G);
 
+    // Every lane group runs its own stream of codewords: as soon as a group's codeword converges (or gives up)
+    // the group writes it out and claims the next frame, while the other groups of the warp carry on with
+    // theirs -- a slow codeword never idles its neighbour.  The warp executes one loop; `have` says whether
+    // this group currently holds a codeword, `iter` is that codeword's iteration.
+    CT Lv[8][EPT], vold[32][EPT];
+    bool have = false, exhausted = false;
+    unsigned long long frame = 0;
+    unsigned iter = 0;
     for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)CWW);
-        base = __shfl_sync(kFull, base, 0);
-        if (base >= batch) break;
-        const unsigned long long frame = base + cwl;
-        const bool live = frame < batch;                 // the second codeword of a TC128 warp may not exist
+        const bool need = !have && !exhausted;
+        unsigned long long claimed = 0;
+        if constexpr (CWW == 1) {                         // one group per warp: `need` is warp-uniform
+            if (need) {
+                if (lane == 0) claimed = atomicAdd(counter, 1ull);
+                claimed = __shfl_sync(kFull, claimed, 0);
+            }
+        } else {
+            if (sl == 0 && need) claimed = atomicAdd(counter, 1ull);
+            claimed = __shfl_sync(kFull, claimed, cwl * G);
+        }
+        if (need && claimed >= batch) exhausted = true;
+        if (need && !exhausted) {
+        frame = claimed;
+        have = true;
+        iter = 0;
         const typename FrontSrc<FRONT, T>::type *llr =
-            llrs_all + (live ? frame : base) * (unsigned long long)(FRONT == kFrontHard ? N / 8 : N);   // front.cuh
-
-        CT Lv[8][EPT], vold[32][EPT];
+            llrs_all + frame * (unsigned long long)(FRONT == kFrontHard ? N / 8 : N);   // front.cuh
 #pragma unroll
         for (int ei = 0; ei < EPT; ei++) {
             const int e = sl + ei * G;
@@ -85,14 +106,20 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
 #pragma unroll
             for (int c = 0; c < 8; c++) hbv[c * M + e] = 0;
         }
+        }
+        if constexpr (CWW == 1) {
+            if (!have) break;
+        } else {
+            if (__all_sync(kFull, !have)) break;         // every group has run out of frames
+        }
         __syncwarp();
 
-        bool done = !live;           // this lane group's codeword is finished (or absent)
+        bool finished = have && max_iters == 0;          // (false, 0) with an all-zero output
         bool ok = false;
-        unsigned iters_run = max_iters;
-        for (unsigned iter = 0; iter < max_iters; iter++) {
+        const bool run = have && !finished;
+        {
             // ---- variable phase ----
-            if (!done) {
+            if (run) {
 #pragma unroll
                 for (int ei = 0; ei < EPT; ei++) {
                     const int j = sl + ei * G;
@@ -129,7 +156,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
             __syncwarp();
             // ---- check phase ----
             bool par_any = false;
-            if (!done) {
+            if (run) {
 #pragma unroll
                 for (int ei = 0; ei < EPT; ei++) {
                     const int i = sl + ei * G;
@@ -200,15 +227,17 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                 }
             }
             const unsigned bad = __ballot_sync(kFull, par_any);
-            if (!done && (bad & group_mask) == 0) {                                       // :453
-                done = true; ok = true; iters_run = iter;                                 // :462
+            if (run) {
+                if ((bad & group_mask) == 0) { finished = true; ok = true; }              // :453, :462 (iters = iter)
+                else if (++iter == max_iters) finished = true;                            // :466-474 (iters = max_iters)
             }
             __syncwarp();
-            if (__all_sync(kFull, done)) break;
         }
 
         // ---- output: hard decisions MSB first (:455-461, :466-473); p = 0 for TC codes ----
-        if (live) {
+        if (finished) {
+            const unsigned iters_run = ok ? iter : (unsigned)max_iters;
+            have = false;
             uint8_t *out = out_all + frame * (unsigned long long)(N / 8);
             for (int o = sl; o < N / 8; o += G) {
                 unsigned byte = 0;
@@ -232,7 +261,7 @@ cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
     TcParams prm{};
     for (int b = 0; b < 32; b++) prm.shift[b] = (uint8_t)c.blocks[b].shift;
-    const size_t warp_bytes = ((sizeof(typename MsgStore<T>::type) * CWW * 32 * M + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
+    const size_t warp_bytes = ((sizeof(typename MsgStore<T>::type) * CWW * tc_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kWarpsPerCta;
     auto kern = decode_ms_tc_kernel<M, T, FRONT>;
     static bool configured[16] = {};
