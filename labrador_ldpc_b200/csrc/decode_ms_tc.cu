@@ -9,11 +9,13 @@
 // of every prototype column (variable side) and every prototype row (check side).  TC128 packs two
 // codewords into one warp.  Messages live in a per-warp slice of shared memory in check order
 // (the variable side reads/writes element (j - shift) mod M of the block), the two phases of an
-// iteration are separated by __syncwarp() only -- no CTA barrier anywhere -- and every warp pulls
-// its next codewords from an atomic counter, so early exits of one warp never stall another.
-// Arithmetic: the scalar DecodeFrom semantics of llr_arith.cuh; saturating adds in ascending edge
-// index per variable (:408); self-correction against the previous v kept in registers (:422-426);
-// min over the other edges by prefix/suffix minima (= min1/min2 selection, :391-395).
+// iteration are separated by __syncwarp() only -- no CTA barrier anywhere -- and every lane group
+// claims its next codeword from an atomic counter the moment its current one converges or gives up,
+// so a slow codeword stalls neither another warp nor the other group of its own warp.
+// Arithmetic: f32 / f64 / i32 use the scalar DecodeFrom semantics of llr_arith.cuh, i8 / i16 the biased
+// representation of biased_arith.cuh; saturating adds in ascending edge index per variable (:408);
+// self-correction against the previous v kept in registers (:422-426); min over the other edges
+// (= min1/min2 selection, :391-395).
 #include <cuda_runtime.h>
 
 #include <type_traits>

@@ -1,10 +1,11 @@
-// Specialised min-sum decoder for the TM codes with one element per lane: i16 / i32 / f32 LLRs
+// Specialised min-sum decoder for the TM codes with one element per lane: i16 / i32 / f32 / f64 LLRs
 // (and every LLR type on TM1280, whose M = 128 is too small for the packed-lane i8 kernel).
 //
 // Replaces LDPCCode::decode_ms::<T> (reference src/decoder.rs:347-475).  Same skeleton as
 // decode_ms_tm.cu -- thread t owns element t of every prototype column and every prototype row,
 // identity-block messages stay in registers, pi_k-block messages go through shared memory in check
-// order, u is never stored, two-stage bit-packed exit test -- but the arithmetic is the plain scalar
+// order, u is never stored, two-stage bit-packed exit test -- with one value per 32-bit register.
+// i8 / i16 use the biased one-instruction arithmetic of biased_arith.cuh; the other types the plain scalar
 // DecodeFrom semantics of llr_arith.cuh (reference src/decoder.rs:42-86):
 //   variable side  va = llr (+) u_0 (+) u_1 ...  in ascending edge index (:408), then v_j = va (-) u_j (:421)
 //   check side     self-correction against the previous v kept in a register (:422-426), min over the
