@@ -115,6 +115,23 @@ int main(void) {
     assert subprocess.call([str(exe)]) == 0
 
 
+def build_example(name, outdir):
+    import labrador_ldpc_b200 as L
+    libdir = os.path.dirname(L._LIB_PATH)
+    exe = os.path.join(str(outdir), name)
+    subprocess.check_call(["gcc", "-Wall", "-Wextra", "-Werror", os.path.join(ROOT, "examples", name + ".c"),
+                           "-I", os.path.join(ROOT, "include"), "-L", libdir, "-llabrador_ldpc", "-lm",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    return exe
+
+
+def test_examples_compile_as_plain_c(tmp_path):
+    """examples/example.c (the reference's capi example pattern) and examples/batch_example.c build with a
+    C compiler against include/labrador_ldpc.h alone; they are run on the GPU box by tests/test_gpu_parity.py."""
+    for name in ("example", "batch_example"):
+        assert os.path.exists(build_example(name, tmp_path))
+
+
 def test_argument_validation_needs_no_gpu(ldpc):
     L = ldpc.lib
     buf = np.zeros(64, np.uint8)

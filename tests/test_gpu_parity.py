@@ -441,6 +441,17 @@ def test_shutdown_and_reinitialise(ldpc, oracle):
     assert_exact(c.decode_bf_batch(rx, 20), oracle.decode_bf_batch(5, rx, 20), "bf after explicit re-init")
 
 
+def test_c_examples_run(tmp_path):
+    """The C programs under examples/ (single-codeword reference-signature calls; batched Monte-Carlo trial)
+    run against the shared library and report success."""
+    import subprocess
+    from test_capi_host import build_example
+    for name in ("example", "batch_example"):
+        res = subprocess.run([build_example(name, tmp_path)], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+    assert "frame errors" in res.stdout
+
+
 def test_launch_counter_and_kernel_names(ldpc):
     before = ldpc.kernel_launch_count()
     c = ldpc.LDPCCode.TC128
