@@ -11,7 +11,10 @@
 //   * "flip every variable whose count equals the maximum" (:276-296) needs the set of counts that occur.
 // A codeword is 16 / 32 / 64 bytes, so a whole decode fits in a thread's registers: no shared memory, no
 // synchronisation, and consecutive threads read consecutive frames (16-byte loads).  Threads of a warp
-// whose codeword has converged idle until the slowest one is done.
+// whose codeword has converged idle until the slowest one is done, and a codeword that never converges runs
+// all max_iters iterations -- so large batches are decoded in two passes: the first stops after kFirstPassIters
+// iterations and puts the few unfinished frames on a list, the second decodes those from scratch with the full
+// iteration budget (same result: the decoder is deterministic and keeps no state between calls).
 #include <cuda_runtime.h>
 
 #include "bf_common.cuh"
@@ -23,6 +26,8 @@ namespace ldpc {
 namespace {
 
 constexpr int kTcBfThreads = 128;
+constexpr unsigned kFirstPassIters = 6;       // covers > 99 % of the frames that converge at all
+constexpr size_t kTwoPassMinBatch = 1u << 18;   // below this a single pass is a few tens of microseconds anyway
 
 template <int M> struct TcWord { typedef uint32_t type; };
 template <> struct TcWord<64> { typedef uint64_t type; };
@@ -35,16 +40,16 @@ template <int M> __device__ __forceinline__ typename TcWord<M>::type rot_right(t
     else return (x >> s) | (x << ((64u - s) & 63u));
 }
 
+// Decodes one frame with at most `iter_limit` iterations.  Returns false -- and writes nothing -- if the frame is
+// still undecided after iter_limit < max_iters iterations (first pass); otherwise writes output / success / iters.
 template <int M>
-__global__ void __launch_bounds__(kTcBfThreads)
-decode_bf_tc_kernel(const TcParams prm, const uint8_t *__restrict__ in_all, uint8_t *__restrict__ out_all,
-                    unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
-                    uint32_t *__restrict__ iters_out) {
+__device__ __forceinline__ bool decode_bf_tc_frame(const TcParams &prm, const uint8_t *__restrict__ in_all,
+                                                   uint8_t *__restrict__ out_all, unsigned long long frame,
+                                                   unsigned max_iters, unsigned iter_limit,
+                                                   uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out) {
     typedef typename TcWord<M>::type W;
     constexpr int NWORDS = M / 4;                     // 32-bit words per codeword (n / 32)
     constexpr W kMask = M == 16 ? (W)0xFFFFu : ~(W)0;
-    const unsigned long long frame = (unsigned long long)blockIdx.x * kTcBfThreads + threadIdx.x;
-    if (frame >= batch) return;
 
     // ---- load: word k = variables 32k .. 32k+31, bit i = variable 32k + i (input is MSB first, :251) ----
     uint32_t r[NWORDS];
@@ -74,7 +79,7 @@ decode_bf_tc_kernel(const TcParams prm, const uint8_t *__restrict__ in_all, uint
 
     unsigned iters_run = max_iters;
     bool ok = false;
-    for (unsigned iter = 0; iter < max_iters; iter++) {
+    for (unsigned iter = 0; iter < iter_limit; iter++) {
         // parity of every check (:269-273)
         W par[4] = {0, 0, 0, 0};
         tc_static_for<0, 32>([&](auto bi) {
@@ -116,6 +121,8 @@ decode_bf_tc_kernel(const TcParams prm, const uint8_t *__restrict__ in_all, uint
         }
     }
 
+    if (!ok && iter_limit < max_iters) return false;   // undecided: the second pass redoes this frame
+
     // ---- store: all n hard decisions, MSB first ----
 #pragma unroll
     for (int c = 0; c < 8; c++) {
@@ -144,20 +151,62 @@ decode_bf_tc_kernel(const TcParams prm, const uint8_t *__restrict__ in_all, uint
     }
     if (success) success[frame] = ok ? 1 : 0;
     if (iters_out) iters_out[frame] = iters_run;
+    return true;
+}
+
+// First (or only) pass: thread t decodes frame t; frames left undecided go on `list` (list[0] = count).
+template <int M>
+__global__ void __launch_bounds__(kTcBfThreads)
+decode_bf_tc_kernel(const TcParams prm, const uint8_t *__restrict__ in_all, uint8_t *__restrict__ out_all,
+                    unsigned long long batch, unsigned max_iters, unsigned iter_limit, uint8_t *__restrict__ success,
+                    uint32_t *__restrict__ iters_out, unsigned *__restrict__ list) {
+    const unsigned long long frame = (unsigned long long)blockIdx.x * kTcBfThreads + threadIdx.x;
+    if (frame >= batch) return;
+    if (!decode_bf_tc_frame<M>(prm, in_all, out_all, frame, max_iters, iter_limit, success, iters_out))
+        list[1 + atomicAdd(&list[0], 1u)] = (unsigned)frame;
+}
+
+// Second pass: the listed frames, full iteration budget.
+template <int M>
+__global__ void __launch_bounds__(kTcBfThreads)
+decode_bf_tc_retry_kernel(const TcParams prm, const uint8_t *__restrict__ in_all, uint8_t *__restrict__ out_all,
+                          unsigned max_iters, uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
+                          const unsigned *__restrict__ list) {
+    const unsigned count = list[0];
+    for (unsigned i = blockIdx.x * kTcBfThreads + threadIdx.x; i < count; i += gridDim.x * kTcBfThreads)
+        decode_bf_tc_frame<M>(prm, in_all, out_all, list[1 + i], max_iters, max_iters, success, iters_out);
 }
 
 template <int M>
-cudaError_t launch_bf_tc(const CodeInfo &c, const uint8_t *input, uint8_t *output, size_t batch, size_t max_iters,
+cudaError_t launch_bf_tc(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input, uint8_t *output, size_t batch, size_t max_iters,
                          uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     TcParams prm{};
     for (int b = 0; b < 32; b++) prm.shift[b] = (uint8_t)c.blocks[b].shift;
     const unsigned long long grid = (batch + kTcBfThreads - 1) / kTcBfThreads;
     if (grid > 0x7FFFFFFFull) return cudaErrorInvalidValue;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    decode_bf_tc_kernel<M><<<(unsigned)grid, kTcBfThreads, 0, stream>>>(prm, input, output, (unsigned long long)batch, mi,
-                                                                         success, iters);
-    count_launch();
-    return cudaGetLastError();
+    if (batch < kTwoPassMinBatch || batch > 0xFFFFFFF0ull || mi <= kFirstPassIters) {
+        decode_bf_tc_kernel<M><<<(unsigned)grid, kTcBfThreads, 0, stream>>>(prm, input, output, (unsigned long long)batch,
+                                                                             mi, mi, success, iters, nullptr);
+        count_launch();
+        return cudaGetLastError();
+    }
+    // two passes; the list lives in stream-ordered memory, so concurrent calls on other streams do not share it
+    unsigned *list = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&list), (batch + 1) * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(list, 0, sizeof(unsigned), stream);
+    if (e == cudaSuccess) {
+        decode_bf_tc_kernel<M><<<(unsigned)grid, kTcBfThreads, 0, stream>>>(prm, input, output, (unsigned long long)batch,
+                                                                             mi, kFirstPassIters, success, iters, list);
+        unsigned long long grid2 = (unsigned long long)ctx.sm_count * 8;
+        if (grid2 > grid) grid2 = grid;
+        decode_bf_tc_retry_kernel<M><<<(unsigned)grid2, kTcBfThreads, 0, stream>>>(prm, input, output, mi, success, iters, list);
+        count_launch(2);
+        e = cudaGetLastError();
+    }
+    const cudaError_t e2 = cudaFreeAsync(list, stream);
+    return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace
@@ -165,14 +214,13 @@ cudaError_t launch_bf_tc(const CodeInfo &c, const uint8_t *input, uint8_t *outpu
 // Returns true (and launches) for the TC codes.
 bool launch_decode_bf_tc(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
                          size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err) {
-    (void)ctx;
     if (code < 0 || code > 2) return false;
     const CodeInfo &c = *code_info(code);
     if (!tc_structure_matches(c)) return false;
     switch (c.m) {
-        case 16: *err = launch_bf_tc<16>(c, input, output, batch, max_iters, success, iters, stream); return true;
-        case 32: *err = launch_bf_tc<32>(c, input, output, batch, max_iters, success, iters, stream); return true;
-        case 64: *err = launch_bf_tc<64>(c, input, output, batch, max_iters, success, iters, stream); return true;
+        case 16: *err = launch_bf_tc<16>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
+        case 32: *err = launch_bf_tc<32>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
+        case 64: *err = launch_bf_tc<64>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
         default: return false;
     }
 }

@@ -305,6 +305,17 @@ def test_decode_bf_ragged_large_and_unaligned_batches(ldpc, oracle):
             got = c.decode_bf_batch(view, 30, output=oview)
             torch.cuda.synchronize()
             assert_exact([g.cpu().numpy() for g in got], want, "%s bf unaligned off=%d" % (NAMES[code], off))
+    # TC codes: batches of 2^18 frames and more are decoded in two passes (undecided frames after 6 iterations are
+    # listed and redone with the full budget); frames with many errors make sure the list is exercised
+    for code in (0, 1, 2):
+        rng = np.random.default_rng(800 + code)
+        parts = [hard_frames(oracle, code, 3000, flips, seed=810 + code + flips)[2] for flips in (0, 2, 5, 9, 14)]
+        rx = np.concatenate(parts)[rng.integers(0, 15000, 300_000)]          # 300 000 frames >= the two-pass threshold
+        want = oracle.decode_bf_batch(code, rx, 40, nthreads=8)
+        assert (want[1] == 0).sum() >= 5 and (want[2][want[1].astype(bool)] > 6).any()   # both kinds reach the list
+        assert_exact(ldpc.LDPCCode(code).decode_bf_batch(rx, 40), want, "%s bf two-pass" % NAMES[code])
+        assert_exact(ldpc.LDPCCode(code).decode_bf_batch(rx, 5), oracle.decode_bf_batch(code, rx, 5, nthreads=8),
+                     "%s bf maxiters below the first-pass cap" % NAMES[code])
     code, batch = 3, 100_000   # > 2 * 148 SMs * 8 warps * 4 * 8 codewords: two groups per claim
     rng = np.random.default_rng(77)
     _, _, small = hard_frames(oracle, code, 4096, 3, seed=700)
