@@ -167,6 +167,9 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
     const int blocks = (dc.n - dc.k) / dc.b;
     int wpt = forced ? forced : (dc.b >= 32 ? (blocks % 8 == 0 ? 8 : 4) : 1);   // measured: profiles/r01_sweep.md
     if (dc.b < 32 || blocks % wpt != 0) wpt = 1;
+    // a handful of frames (the single-codeword API): latency matters, not instruction count -- one parity word per
+    // thread puts 8x as many threads on each frame
+    if (!forced && batch * (size_t)((dc.n - dc.k) / 32 / wpt) < (size_t)ctx.sm_count * 32) wpt = 1;
     switch (wpt) {
         case 8: return launch_encode_wpt<8>(ctx, dc, data, codewords, batch, stream);
         case 4: return launch_encode_wpt<4>(ctx, dc, data, codewords, batch, stream);
