@@ -25,12 +25,14 @@ __all__ = ["LDPCCode", "LdpcError", "lib", "LLR_TYPES", "init", "shutdown", "ker
            "decode_ms_mixed"]
 
 _LIB_PATH = _build.LIB
-if os.path.exists(_LIB_PATH) and _build.needs_build() and os.environ.get("LABRADOR_LDPC_NO_REBUILD") != "1":
-    # the shared object is older than the sources: rebuild rather than run a stale binary
+if _build.needs_build() and os.environ.get("LABRADOR_LDPC_NO_REBUILD") != "1":
+    # the shared object is missing (fresh checkout) or older than the sources: (re)build it with nvcc rather than
+    # run without it or with a stale binary.  This is the in-tree build, not a fallback: if it fails the import fails.
     try:
         _build.build()
     except Exception as exc:   # pragma: no cover
-        raise ImportError("labrador_ldpc_b200: liblabrador_ldpc.so is stale and rebuilding failed: %s" % exc)
+        raise ImportError("labrador_ldpc_b200: liblabrador_ldpc.so is missing or stale and building it failed "
+                          "(there is no CPU fallback): %s" % exc)
 if not os.path.exists(_LIB_PATH):
     raise ImportError(
         "labrador_ldpc_b200: %s is missing -- build it with `python -m labrador_ldpc_b200._build` "

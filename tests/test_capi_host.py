@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -130,6 +131,28 @@ def test_examples_compile_as_plain_c(tmp_path):
     C compiler against include/labrador_ldpc.h alone; they are run on the GPU box by tests/test_gpu_parity.py."""
     for name in ("example", "batch_example"):
         assert os.path.exists(build_example(name, tmp_path))
+
+
+def test_fresh_checkout_builds_on_import(ldpc, tmp_path):
+    """A checkout has no lib/ (the .so is git-ignored): importing the package -- which is what
+    __graft_entry__.build() does first -- must run the in-tree build instead of failing.  Checked on a copy of
+    the package whose build step is replaced by "copy the real .so" so the test stays fast."""
+    import shutil
+    pkg = tmp_path / "labrador_ldpc_b200"
+    shutil.copytree(os.path.join(ROOT, "labrador_ldpc_b200"), pkg,
+                    ignore=shutil.ignore_patterns("lib", "build", "__pycache__"))
+    shutil.copytree(os.path.join(ROOT, "include"), tmp_path / "include")
+    assert not (pkg / "lib").exists()
+    with open(pkg / "_build.py", "a") as f:
+        f.write("\n\ndef build(force=False, verbose=False):\n"
+                "    os.makedirs(LIBDIR, exist_ok=True)\n"
+                "    shutil.copy(%r, LIB)\n"
+                "    open(LIB + '.stamp', 'w').write(_stamp())\n"
+                "    return LIB\n" % ldpc._LIB_PATH)
+    out = subprocess.check_output([sys.executable, "-c",
+                                   "import sys; sys.path.insert(0, %r); import labrador_ldpc_b200 as L; "
+                                   "print(L._LIB_PATH); print(L.version())" % str(tmp_path)], text=True)
+    assert str(pkg / "lib") in out and "labrador-ldpc-b200" in out
 
 
 def test_argument_validation_needs_no_gpu(ldpc):
