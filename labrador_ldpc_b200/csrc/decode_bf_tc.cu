@@ -191,10 +191,29 @@ cudaError_t launch_bf_tc(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
         count_launch();
         return cudaGetLastError();
     }
-    // two passes; the list lives in stream-ordered memory, so concurrent calls on other streams do not share it
-    unsigned *list = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&list), (batch + 1) * sizeof(unsigned), stream);
-    if (e != cudaSuccess) return e;
+    // two passes.  The list of undecided frames is a grow-only buffer of the device context (launchers run under the
+    // context mutex); an event makes a call on another stream wait for the previous user of the list.
+    const size_t need = (batch + 1) * sizeof(unsigned);
+    cudaError_t e = cudaSuccess;
+    if (!ctx.retry_done) {
+        e = cudaEventCreateWithFlags(&ctx.retry_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    } else {
+        e = cudaStreamWaitEvent(stream, ctx.retry_done, 0);
+        if (e != cudaSuccess) return e;
+    }
+    if (ctx.retry_list_bytes < need) {
+        if (ctx.retry_list) {
+            cudaEventSynchronize(ctx.retry_done);
+            cudaFree(ctx.retry_list);
+            ctx.retry_list = nullptr;
+            ctx.retry_list_bytes = 0;
+        }
+        e = cudaMalloc(reinterpret_cast<void **>(&ctx.retry_list), need);
+        if (e != cudaSuccess) return e;
+        ctx.retry_list_bytes = need;
+    }
+    unsigned *list = ctx.retry_list;
     e = cudaMemsetAsync(list, 0, sizeof(unsigned), stream);
     if (e == cudaSuccess) {
         decode_bf_tc_kernel<M><<<(unsigned)grid, kTcBfThreads, 0, stream>>>(prm, input, output, (unsigned long long)batch,
@@ -205,7 +224,7 @@ cudaError_t launch_bf_tc(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
         count_launch(2);
         e = cudaGetLastError();
     }
-    const cudaError_t e2 = cudaFreeAsync(list, stream);
+    const cudaError_t e2 = cudaEventRecord(ctx.retry_done, stream);
     return e != cudaSuccess ? e : e2;
 }
 

@@ -199,6 +199,8 @@ void runtime_shutdown() {
             if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
         }
         if (c->vscratch) cudaFree(c->vscratch);
+        if (c->retry_done) { cudaEventSynchronize(c->retry_done); cudaEventDestroy(c->retry_done); }
+        if (c->retry_list) cudaFree(c->retry_list);
         if (c->table_blob) cudaFree(c->table_blob);
     }
     r.ctxs.clear();

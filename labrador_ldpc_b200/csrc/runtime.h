@@ -59,6 +59,11 @@ struct DeviceCtx {
     // scratch for decode paths whose message array does not fit in shared memory
     void *vscratch = nullptr;
     size_t vscratch_bytes = 0;
+    // list of undecided frames of the two-pass TC bit-flipping decoder (decode_bf_tc.cu); `retry_done` orders
+    // its reuse across streams
+    unsigned *retry_list = nullptr;
+    size_t retry_list_bytes = 0;
+    cudaEvent_t retry_done = nullptr;
     // host-pointer pipeline
     static constexpr int kPipe = 3;
     cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
