@@ -2,6 +2,7 @@
 #include "code_tables.h"
 
 #include <mutex>
+#include <utility>
 
 #include "ccsds_tables.h"
 
@@ -135,6 +136,68 @@ void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::ve
         var_tab[(size_t)vfill[a]++ * c.vars + a] = idx | (ch << 16);
         chk_tab[(size_t)cfill[ch]++ * c.checks + ch] = idx | (a << 16);
     }
+}
+
+bool tm_encoder_table(int code, std::vector<uint32_t> &out) {
+    out.clear();
+    const CodeInfo *ci = code_info(code);
+    if (!ci || ci->p == 0 || ci->rows != 3 || ci->m % 128 != 0 || ci->n - ci->k != 2 * ci->m) return false;
+    const CodeInfo &c = *ci;
+    const int M = c.m, Q = M / 4, QW = Q / 32;
+    const int CA = c.cols - 3, CB = c.cols - 2, CC = c.cols - 1;
+    // structure check: which blocks sit in the three parity columns
+    std::vector<const Block *> s_blocks, g_blocks;     // S = row 2 / col CB,  G = row 1 / col CC
+    int ident_ok = 0;
+    for (int bi = 0; bi < c.n_blocks; bi++) {
+        const Block &b = c.blocks[bi];
+        const bool ident = b.kind == kIdentity && b.shift == 0;
+        if (b.col == CA) { if (b.row != 0 || !ident) return false; ident_ok |= 1; }
+        else if (b.col == CB) {
+            if (b.row == 1) { if (!ident) return false; ident_ok |= 2; }
+            else if (b.row == 2) s_blocks.push_back(&b);
+            else return false;
+        } else if (b.col == CC) {
+            if (b.row == 1) g_blocks.push_back(&b);
+            else if (b.row == 2) { if (!ident) return false; ident_ok |= 4; }
+        } else if (b.row == 0) return false;            // row 0 has no data terms
+    }
+    if (ident_ok != 7 || s_blocks.empty() || g_blocks.empty()) return false;
+    // A = I + S G as bit rows, augmented with the four right-hand sides e_{qj Q}
+    const int RW = M / 64 + 1;
+    std::vector<uint64_t> a((size_t)M * RW, 0);
+    auto flip = [&](int r, int col) { a[(size_t)r * RW + (col >> 6)] ^= 1ull << (col & 63); };
+    for (int i = 0; i < M; i++) {
+        flip(i, i);
+        for (const Block *s : s_blocks)
+            for (const Block *g : g_blocks) flip(i, block_pi(c, *g, block_pi(c, *s, i)));
+    }
+    for (int qj = 0; qj < 4; qj++) flip(qj * Q, M + qj);
+    // Gauss-Jordan over GF(2)
+    for (int col = 0; col < M; col++) {
+        int piv = -1;
+        for (int r = col; r < M; r++)
+            if ((a[(size_t)r * RW + (col >> 6)] >> (col & 63)) & 1) { piv = r; break; }
+        if (piv < 0) return false;
+        if (piv != col)
+            for (int w = 0; w < RW; w++) std::swap(a[(size_t)piv * RW + w], a[(size_t)col * RW + w]);
+        const uint64_t *prow = &a[(size_t)col * RW];
+        const int w0 = col >> 6;
+        for (int r = 0; r < M; r++) {
+            if (r == col) continue;
+            uint64_t *row = &a[(size_t)r * RW];
+            if ((row[w0] >> (col & 63)) & 1)
+                for (int w = w0; w < RW; w++) row[w] ^= prow[w];
+        }
+    }
+    out.assign((size_t)16 * QW, 0);
+    for (int qi = 0; qi < 4; qi++)
+        for (int qj = 0; qj < 4; qj++)
+            for (int z = 0; z < Q; z++) {
+                const int bit = M + qj;
+                if ((a[(size_t)(qi * Q + z) * RW + (bit >> 6)] >> (bit & 63)) & 1)
+                    out[(size_t)(qi * 4 + qj) * QW + (z >> 5)] |= 1u << (z & 31);
+            }
+    return true;
 }
 
 }  // namespace ldpc

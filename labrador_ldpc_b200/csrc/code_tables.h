@@ -65,4 +65,18 @@ uint32_t edge_crc(const CodeInfo &c);
 // Missing entries are kNoEdge.
 void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::vector<uint32_t> &chk_tab);
 
+// Table of the parity-check-based TM encoder (encode_tm.cu).  In every TM prototype the three parity block
+// columns (CA, CB transmitted, CC punctured) sit in H as
+//     row 0:  I(CA)                +  (I + P0)(CC)
+//     row 1:  [data]  +  I(CB)     +  (P1 + P2 + P3)(CC)
+//     row 2:  [data]  +  S(CB)     +  I(CC)              S = P6 + P7
+// so with t1 / t2 = the data terms of rows 1 / 2:  A * p_CC = t2 + S t1,  A = I + S (P1 + P2 + P3), and then
+// p_CB = t1 + (P1 + P2 + P3) p_CC, p_CA = (I + P0) p_CC.  Every pi_k maps quarter to quarter by a rotation, so A^-1
+// is a 4 x 4 array of Q x Q circulants (Q = M/4) and is fully described by the first column of each:
+//     out[(qi * 4 + qj) * (Q / 32) + w], bit t  =  A^-1 [qi * Q + 32 w + t] [qj * Q]
+// (Q = 32 for M = 128: one word).  Returns false (out empty) if the code is not a TM code with this structure or
+// A is singular.  The result is the same systematic codeword the compact generator produces (the parity part of
+// H is invertible, so the parity bits of a data word are unique); tests compare the two bit for bit.
+bool tm_encoder_table(int code, std::vector<uint32_t> &out);
+
 }  // namespace ldpc

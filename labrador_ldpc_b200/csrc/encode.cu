@@ -157,11 +157,21 @@ cudaError_t launch_encode_wpt(DeviceCtx &ctx, const DeviceCode &dc, const uint8_
 
 }  // namespace
 
+bool launch_encode_tm(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t *codewords, size_t batch,
+                      cudaStream_t stream, cudaError_t *err);   // encode_tm.cu
+
 cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t *codewords, size_t batch,
                           cudaStream_t stream) {
     const DeviceCode &dc = ctx.codes[code];
     if (data == codewords) data = nullptr;
     if (batch == 0) return cudaSuccess;
+    // TM codes: through the sparse parity-check matrix (encode_tm.cu), 4-16x fewer bit operations than the generator;
+    // LABRADOR_LDPC_ENC_GENERATOR=1 keeps the generator kernel below for A/B runs and tests
+    static const bool force_gen = [] { const char *e = getenv("LABRADOR_LDPC_ENC_GENERATOR"); return e && atoi(e) != 0; }();
+    if (!force_gen) {
+        cudaError_t err = cudaSuccess;
+        if (launch_encode_tm(ctx, code, data, codewords, batch, stream, &err)) return err;
+    }
     // words per thread: the number of circulant blocks per row (n-k)/b must be divisible by it
     static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_ENC_WPT"); return e ? atoi(e) : 0; }();
     const int blocks = (dc.n - dc.k) / dc.b;

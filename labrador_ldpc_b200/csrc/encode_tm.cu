@@ -1,0 +1,309 @@
+// Batched systematic encoder for the TM codes through the SPARSE parity-check matrix.
+//
+// Replaces EncodeInto::encode_parity / LDPCCode::encode / copy_encode (reference src/encoder.rs:41-82,
+// 107-160, 189-252, 292-315) for TM1280 ... TM8192.  The reference multiplies the data by the dense
+// generator: k * (n-k) bit operations per codeword (16.8 M for TM8192).  The codeword is the unique
+// solution of H c = 0 with the given data bits, so it can equally be computed from H, which is sparse
+// except for ONE M x M inverse (code_tables.h: tm_encoder_table):
+//     t1, t2 = data terms of check rows 1 and 2              (sparse: windows of the data words)
+//     s      = t2 + S t1,  S = the row-2 blocks of column CB  (sparse)
+//     p_CC   = A^-1 s,     A = I + S G, G = the row-1 blocks of column CC   (dense, M^2 bit operations)
+//     p_CB   = t1 + G p_CC,   p_CA = (I + P0) p_CC            (sparse)
+// (CA, CB = the two transmitted parity block columns, CC = the punctured one.)  M^2 is 4x (rate 1/2),
+// 8x (rate 2/3) and 16x (rate 4/5) less than k * (n-k).  The result is bit-identical to the generator
+// encoder (tests/test_gpu_parity.py compares both with the oracle and with each other).
+//
+// Layout: as in decode_bf_tm.cu -- one codeword per group of min(32, M/32) lanes, bit-packed (bit i of word
+// w = element 32 w + i), each lane owning one word (M = 2048: two) of every block column; identity blocks
+// connect a lane's own words, pi_k blocks read a 32-bit window lo[i] : hi[i] from shared memory.  A^-1 is
+// a 4 x 4 array of Q x Q circulants, kept as 16 first columns (<= 1 KB) in shared memory: every set bit y of
+// s XORs the window of the column rotated by y (one funnel shift) into the lane's words of p_CC.
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+#include "runtime.h"
+#include "tm_common.cuh"
+
+namespace ldpc {
+using namespace tm;
+
+namespace {
+
+constexpr int kEncWarps = 8;
+
+template <class P> __host__ __device__ constexpr int n_blocks_at(int r, int c) {
+    int n = 0;
+    for (int b = 0; b < P::NB; b++) n += (P::blk(b).row == r && P::blk(b).col == c);
+    return n;
+}
+template <class P> __host__ __device__ constexpr int n_pblocks_at(int r, int c) {
+    int n = 0;
+    for (int b = 0; b < P::NB; b++) n += (P::blk(b).row == r && P::blk(b).col == c && P::blk(b).isp);
+    return n;
+}
+
+// shared-memory slot of a block column: data columns first, then CB (holds t1), then CC (holds p_CC)
+template <class P> __host__ __device__ constexpr int slot_of(int col) {
+    return col < P::NCOL - 3 ? col : (col == P::NCOL - 2 ? P::NCOL - 3 : P::NCOL - 2);
+}
+
+template <class P, int M> __host__ __device__ constexpr int enc_cw_stride() {
+    constexpr int MW = M / 32, LPC = MW < 32 ? MW : 32;
+    constexpr int words = 2 * (P::NCOL - 1) * MW;      // lo[] + hi[] of KC + 2 slots
+    return LPC == 32 ? words : ((words + 31) / 32) * 32 + LPC;
+}
+// A^-1 first columns: [qi][qj][QW] with 5 QW words per qi so the four quarters fall into disjoint banks
+template <int M> __host__ __device__ constexpr int enc_tab_words() { return ((4 * 5 * (M / 128) + 31) / 32) * 32; }
+
+__device__ __forceinline__ uint32_t load_be32(const uint8_t *p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+
+template <int RATE, int M>
+__global__ void __launch_bounds__(32 * kEncWarps)
+encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const uint8_t *__restrict__ data_all,
+                 uint8_t *__restrict__ cw_all, unsigned long long batch) {
+    typedef Proto<RATE> P;
+    constexpr int NB = P::NB, NCOL = P::NCOL;
+    constexpr int KC = NCOL - 3, CA = NCOL - 3, CB = NCOL - 2, CC = NCOL - 1;
+    constexpr int NP = count_p<P>(NB);
+    constexpr int Q = M / 4, QW = Q / 32, MW = M / 32;
+    constexpr int LPC = MW < 32 ? MW : 32;                // lanes per codeword
+    constexpr int CWW = 32 / LPC;                         // codewords per warp
+    constexpr int WPL = MW / LPC;                         // words per lane per block column
+    constexpr int SLOTW = (KC + 2) * MW;
+    constexpr int STRIDE = enc_cw_stride<P, M>();
+    constexpr int TABW = enc_tab_words<M>();
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    static_assert(Q % 32 == 0 && (QW & (QW - 1)) == 0 && MW % LPC == 0, "quarters are whole words");
+    // the structure the derivation above rests on (code_tables.cpp checks the same on the run-time tables)
+    static_assert(n_blocks_at<P>(0, CA) == 1 && n_pblocks_at<P>(0, CA) == 0 && n_blocks_at<P>(1, CA) == 0 &&
+                  n_blocks_at<P>(2, CA) == 0, "column CA: identity in row 0 only");
+    static_assert(n_blocks_at<P>(0, CB) == 0 && n_blocks_at<P>(1, CB) == 1 && n_pblocks_at<P>(1, CB) == 0 &&
+                  n_blocks_at<P>(2, CB) == n_pblocks_at<P>(2, CB), "column CB: identity in row 1, pi_k blocks in row 2");
+    static_assert(n_blocks_at<P>(0, CC) == 2 && n_pblocks_at<P>(0, CC) == 1 &&
+                  n_blocks_at<P>(1, CC) == n_pblocks_at<P>(1, CC) && n_blocks_at<P>(2, CC) == 1 &&
+                  n_pblocks_at<P>(2, CC) == 0, "column CC: I + pi in row 0, pi_k blocks in row 1, identity in row 2");
+
+    extern __shared__ __align__(16) uint32_t smem_enc[];
+    uint32_t *tab = smem_enc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / LPC, wl = lane % LPC;
+    uint32_t *lo = smem_enc + TABW + (warp * CWW + grp) * STRIDE;
+    uint32_t *hi = lo + SLOTW;
+
+    for (int i = threadIdx.x; i < 16 * QW; i += blockDim.x) {
+        const int qi = i / (4 * QW);
+        tab[qi * 5 * QW + (i - qi * 4 * QW)] = ainv[i];
+    }
+    __syncthreads();
+
+    // windows of this lane's check words into the variable bits of each pi_k block: (word index << 5) | bit shift
+    uint32_t win[NP > 0 ? NP : 1][WPL];
+#pragma unroll
+    for (int wi = 0; wi < WPL; wi++) {
+        const int e0 = (wl + wi * LPC) * 32, qa = e0 / Q, off = e0 % Q;
+        static_for<0, NB>([&](auto bi) {
+            constexpr int b = decltype(bi)::value;
+            if constexpr (P::blk(b).isp) {
+                const int qv = ((int)prm.theta[b] + qa) & 3;
+                const int s0 = ((int)prm.phi[b][qa] + off) & (Q - 1);
+                win[count_p<P>(b)][wi] = (uint32_t)(((slot_of<P>(P::blk(b).col) * MW + qv * QW + (s0 >> 5)) << 5) | (s0 & 31));
+            }
+        });
+    }
+    auto store_word = [&](int base, int w, uint32_t v) {
+        lo[base + w] = v;
+        hi[base + ((w & ~(QW - 1)) | ((w - 1) & (QW - 1)))] = v;
+    };
+    auto window = [&](uint32_t t) {
+        const uint32_t i = t >> 5;
+        return __funnelshift_r(lo[i], hi[i], t);
+    };
+
+    const unsigned long long n_groups = (batch + CWW - 1) / CWW;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(cw_all) | reinterpret_cast<uintptr_t>(data_all)) & 3u) == 0;
+    const unsigned long long in_stride = data_all ? (unsigned long long)(KC * MW * 4) : (unsigned long long)((KC + 2) * MW * 4);
+    const uint8_t *in_base = data_all ? data_all : cw_all;
+
+    for (unsigned long long g = (unsigned long long)blockIdx.x * kEncWarps + warp; g < n_groups;
+         g += (unsigned long long)gridDim.x * kEncWarps) {
+        const unsigned long long first = g * CWW;
+        const unsigned long long frame = first + grp;
+        const bool live = frame < batch;
+        const uint8_t *in = in_base + (live ? frame : first) * in_stride;
+        uint8_t *cw = cw_all + (live ? frame : first) * (unsigned long long)((KC + 2) * MW * 4);
+
+        // data words (bit-reversed: bit i of word w = element 32 w + i); copy_encode also writes them out
+        uint32_t dw[KC][WPL];
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++) {
+            const int w = wl + wi * LPC;
+#pragma unroll
+            for (int c = 0; c < KC; c++) {
+                const int iw = c * MW + w;
+                uint32_t be;
+                if (aligned) {
+                    const uint32_t raw = reinterpret_cast<const uint32_t *>(in)[iw];
+                    if (data_all && live) reinterpret_cast<uint32_t *>(cw)[iw] = raw;
+                    be = __byte_perm(raw, 0, 0x0123);
+                } else {
+                    be = load_be32(in + 4 * iw);
+                    if (data_all && live) {
+                        cw[4 * iw + 0] = (uint8_t)(be >> 24); cw[4 * iw + 1] = (uint8_t)(be >> 16);
+                        cw[4 * iw + 2] = (uint8_t)(be >> 8);  cw[4 * iw + 3] = (uint8_t)be;
+                    }
+                }
+                dw[c][wi] = __brev(be);
+                store_word(c * MW, w, dw[c][wi]);
+            }
+        }
+        __syncwarp();
+
+        // t1 / t2: data terms of check rows 1 and 2
+        uint32_t t1[WPL], sv[WPL];
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++) {
+            uint32_t x1 = 0, x2 = 0;
+            static_for<0, NB>([&](auto bi) {
+                constexpr int b = decltype(bi)::value;
+                if constexpr (P::blk(b).col < KC) {
+                    uint32_t v;
+                    if constexpr (P::blk(b).isp) v = window(win[count_p<P>(b)][wi]);
+                    else v = dw[P::blk(b).col][wi];
+                    if constexpr (P::blk(b).row == 1) x1 ^= v; else x2 ^= v;
+                }
+            });
+            t1[wi] = x1; sv[wi] = x2;
+            store_word(KC * MW, wl + wi * LPC, x1);          // t1 stands in for column CB
+        }
+        __syncwarp();
+        // s = t2 + S t1
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++) {
+            static_for<0, NB>([&](auto bi) {
+                constexpr int b = decltype(bi)::value;
+                if constexpr (P::blk(b).col == CB && P::blk(b).row == 2) sv[wi] ^= window(win[count_p<P>(b)][wi]);
+            });
+        }
+
+        // p_CC = A^-1 s:  p[qi Q + x] = XOR over qj, y of col_{qi,qj}[(x - y) mod Q] s[qj Q + y]
+        uint32_t pc[WPL];
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++) pc[wi] = 0;
+#pragma unroll
+        for (int wj = 0; wj < WPL; wj++) {
+#pragma unroll 2
+            for (int l = 0; l < LPC; l++) {
+                uint32_t D = __shfl_sync(kFull, sv[wj], grp * LPC + l);
+                const int j = l + wj * LPC, qj = j / QW, wq = j % QW;
+                uint32_t xl[WPL], xh[WPL];
+#pragma unroll
+                for (int wi = 0; wi < WPL; wi++) {
+                    const int w = wl + wi * LPC, qi = w / QW, wx = w % QW;
+                    const int w0 = (wx - wq) & (QW - 1);
+                    const uint32_t *col = tab + qi * 5 * QW + qj * QW;
+                    xh[wi] = col[w0];
+                    xl[wi] = col[(w0 - 1) & (QW - 1)];
+                }
+                while (D) {
+                    const int o = __ffs((int)D) - 1;
+                    D &= D - 1;
+#pragma unroll
+                    for (int wi = 0; wi < WPL; wi++) pc[wi] ^= __funnelshift_l(xl[wi], xh[wi], o);
+                }
+            }
+        }
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++) store_word((KC + 1) * MW, wl + wi * LPC, pc[wi]);
+        __syncwarp();
+
+        // p_CB = t1 + G p_CC,  p_CA = (I + P0) p_CC
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++) {
+            uint32_t pa = 0, pb = t1[wi];
+            static_for<0, NB>([&](auto bi) {
+                constexpr int b = decltype(bi)::value;
+                if constexpr (P::blk(b).col == CC && P::blk(b).row == 1) pb ^= window(win[count_p<P>(b)][wi]);
+                if constexpr (P::blk(b).col == CC && P::blk(b).row == 0) {
+                    if constexpr (P::blk(b).isp) pa ^= window(win[count_p<P>(b)][wi]);
+                    else pa ^= pc[wi];
+                }
+            });
+            if (live) {
+                const int w = wl + wi * LPC;
+                const uint32_t ra = __brev(pa), rb = __brev(pb);
+                if (aligned) {
+                    reinterpret_cast<uint32_t *>(cw)[KC * MW + w] = __byte_perm(ra, 0, 0x0123);
+                    reinterpret_cast<uint32_t *>(cw)[(KC + 1) * MW + w] = __byte_perm(rb, 0, 0x0123);
+                } else {
+                    uint8_t *o = cw + 4 * (KC * MW + w);
+                    o[0] = (uint8_t)(ra >> 24); o[1] = (uint8_t)(ra >> 16); o[2] = (uint8_t)(ra >> 8); o[3] = (uint8_t)ra;
+                    o = cw + 4 * ((KC + 1) * MW + w);
+                    o[0] = (uint8_t)(rb >> 24); o[1] = (uint8_t)(rb >> 16); o[2] = (uint8_t)(rb >> 8); o[3] = (uint8_t)rb;
+                }
+            }
+        }
+        __syncwarp();      // the next codeword overwrites the slots
+    }
+}
+
+template <int RATE, int M>
+cudaError_t launch_enc_tm(DeviceCtx &ctx, const CodeInfo &c, const DeviceCode &dc, const uint8_t *data,
+                          uint8_t *codewords, size_t batch, cudaStream_t stream) {
+    typedef Proto<RATE> P;
+    const TmParams prm = make_params<RATE>(c);
+    constexpr int MW = M / 32, CWW = MW < 32 ? 32 / MW : 1;
+    const size_t smem = ((size_t)enc_tab_words<M>() + (size_t)kEncWarps * CWW * enc_cw_stride<P, M>()) * sizeof(uint32_t);
+    auto kern = encode_tm_kernel<RATE, M>;
+    static bool configured[16] = {};
+    static int per_sm_cached[16] = {};
+    if (!configured[ctx.device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kEncWarps, smem);
+        if (e != cudaSuccess) return e;
+        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device & 15] = true;
+    }
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    const unsigned long long groups = (batch + CWW - 1) / CWW;
+    const unsigned long long need = (groups + kEncWarps - 1) / kEncWarps;
+    if (grid > need) grid = need;
+    if (grid == 0) grid = 1;
+    kern<<<(unsigned)grid, 32 * kEncWarps, smem, stream>>>(prm, dc.enc_ainv, data, codewords, (unsigned long long)batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Returns true (and launches) for the TM codes whose parity-check-based encoder table exists.
+bool launch_encode_tm(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t *codewords, size_t batch,
+                      cudaStream_t stream, cudaError_t *err) {
+    if (code < 3 || code > 8) return false;
+    const DeviceCode &dc = ctx.codes[code];
+    if (!dc.enc_ainv) return false;
+    const CodeInfo &c = *code_info(code);
+    switch (code) {
+        case 3: if (!structure_matches<2>(c) || c.m != 128) return false;
+                *err = launch_enc_tm<2, 128>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 4: if (!structure_matches<1>(c) || c.m != 256) return false;
+                *err = launch_enc_tm<1, 256>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 5: if (!structure_matches<0>(c) || c.m != 512) return false;
+                *err = launch_enc_tm<0, 512>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 6: if (!structure_matches<2>(c) || c.m != 512) return false;
+                *err = launch_enc_tm<2, 512>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 7: if (!structure_matches<1>(c) || c.m != 1024) return false;
+                *err = launch_enc_tm<1, 1024>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 8: if (!structure_matches<0>(c) || c.m != 2048) return false;
+                *err = launch_enc_tm<0, 2048>(ctx, c, dc, data, codewords, batch, stream); return true;
+        default: return false;
+    }
+}
+
+}  // namespace ldpc

@@ -84,7 +84,7 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 
     std::vector<unsigned char> blob;
-    struct Off { size_t var_tab, chk_tab, gen, gen32; };
+    struct Off { size_t var_tab, chk_tab, gen, gen32, ainv; bool has_ainv; };
     Off offs[kNumCodes];
     for (int ci = 0; ci < kNumCodes; ci++) {
         const CodeInfo &c = *code_info(ci);
@@ -106,6 +106,9 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
             g32[2 * i + 1] = (uint32_t)(c.gen[i] & 0xFFFFFFFFu);
         }
         offs[ci].gen32 = append(g32.data(), g32.size() * 4);
+        std::vector<uint32_t> ainv;
+        offs[ci].has_ainv = tm_encoder_table(ci, ainv);
+        offs[ci].ainv = offs[ci].has_ainv ? append(ainv.data(), ainv.size() * 4) : 0;
     }
     CUDA_TRY(cudaMalloc(&ctx->table_blob, blob.size()));
     CUDA_TRY(cudaMemcpy(ctx->table_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -121,6 +124,7 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         d.chk_tab = reinterpret_cast<const uint32_t *>(base + offs[ci].chk_tab);
         d.gen = reinterpret_cast<const uint64_t *>(base + offs[ci].gen);
         d.gen32 = reinterpret_cast<const uint32_t *>(base + offs[ci].gen32);
+        d.enc_ainv = offs[ci].has_ainv ? reinterpret_cast<const uint32_t *>(base + offs[ci].ainv) : nullptr;
     }
     for (int i = 0; i < DeviceCtx::kPipe; i++)
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));

@@ -48,6 +48,7 @@ struct DeviceCode {
     const uint32_t *chk_tab;   // [max_check_degree][checks] idx | var << 16
     const uint64_t *gen;       // compact generator rows
     const uint32_t *gen32;     // same rows as big-endian-ordered 32-bit words
+    const uint32_t *enc_ainv;  // TM codes: first columns of the circulants of A^-1 (code_tables.h: tm_encoder_table), else null
 };
 
 struct DeviceCtx {

@@ -168,6 +168,57 @@ def test_encode_kat_and_random(ldpc, oracle, kats, code):
     # linearity over GF(2): enc(a ^ b) == enc(a) ^ enc(b)
     x = c.copy_encode_batch(d[2:3] ^ d[3:4])
     assert np.array_equal(x[0], want[2] ^ want[3])
+    # ragged batches: the TM encoder packs up to eight codewords into a warp
+    for b in (1, 2, 3, 5, 8, 9, 31, 33):
+        assert np.array_equal(c.copy_encode_batch(d[:b]), want[:b]), b
+
+
+@pytest.mark.parametrize("code", [3, 5, 6, 8])
+def test_encode_large_batch_and_unaligned(ldpc, oracle, code):
+    """Grid-stride path of the encoders (more codeword groups than resident warps) and byte-granular
+    pointers (plain-load path), against the oracle."""
+    import torch
+    c = ldpc.LDPCCode(code)
+    kb, nb = c.k() // 8, c.n() // 8
+    batch = 40000 if code in (3, 5) else 12001
+    rng = np.random.default_rng(100 + code)
+    d = rng.integers(0, 256, (batch, kb), dtype=np.uint8)
+    want = oracle.copy_encode_batch(code, d, nthreads=os.cpu_count() or 1)
+    dev = torch.from_numpy(d).cuda()
+    got = c.copy_encode_batch(dev)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), want)
+    # unaligned device buffers (offset 1 and 2 bytes)
+    small = 67
+    src = torch.zeros(small * kb + 8, dtype=torch.uint8, device="cuda")
+    dst = torch.zeros(small * nb + 8, dtype=torch.uint8, device="cuda")
+    src[1:1 + small * kb] = dev[:small].reshape(-1)
+    c.copy_encode_batch(src[1:1 + small * kb].view(small, kb), dst[2:2 + small * nb].view(small, nb))
+    torch.cuda.synchronize()
+    assert np.array_equal(dst[2:2 + small * nb].view(small, nb).cpu().numpy(), want[:small])
+    assert int(dst[:2].sum()) == 0 and int(dst[2 + small * nb:].sum()) == 0
+
+
+def test_generator_encoder_stays_exact():
+    """The TM codes are encoded through the parity-check matrix (encode_tm.cu); the generator kernel
+    (LABRADOR_LDPC_ENC_GENERATOR=1) is the A/B reference and must stay bit-exact as well."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle")
+import labrador_ldpc_b200 as L, pyoracle
+o = pyoracle.Oracle()
+for code in range(3, 9):
+    c = L.LDPCCode(code)
+    d = np.random.default_rng(code).integers(0, 256, (300, c.k() // 8), dtype=np.uint8)
+    assert np.array_equal(c.copy_encode_batch(d), o.copy_encode_batch(code, d, nthreads=4)), code
+print("OK")
+''' % (root, root)
+    env = dict(os.environ, LABRADOR_LDPC_ENC_GENERATOR="1")
+    out = subprocess.check_output([sys.executable, "-c", script], env=env, text=True)
+    assert "OK" in out
 
 
 @pytest.mark.parametrize("code", CODES)
