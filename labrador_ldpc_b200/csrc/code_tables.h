@@ -79,4 +79,13 @@ void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::ve
 // H is invertible, so the parity bits of a data word are unique); tests compare the two bit for bit.
 bool tm_encoder_table(int code, std::vector<uint32_t> &out);
 
+// The same A^-1 as a nibble lookup table ("four Russians"): for every source quarter qj, nibble position
+// nib (0..7) inside a 32-bit word of s and nibble value v, the XOR of the (up to four) rotated columns those
+// bits select, for word offset 0:
+//     lut[((qj * 8 + nib) * 16 + v) * (M / 32) + qi * (Q / 32) + w], bit t
+//         = XOR over bits e of v of  A^-1 [qi * Q + (32 w + t - 4 nib - e) mod Q] [qj * Q]
+// A word of s at in-quarter word index wq then contributes lut[..][(w - wq) mod (Q/32)] to word w of quarter qi
+// of the product.  512 rows of M bits: 8 KB (M = 128) ... 128 KB (M = 2048).
+bool tm_encoder_lut(int code, std::vector<uint32_t> &lut);
+
 }  // namespace ldpc

@@ -16,8 +16,12 @@
 // Layout: as in decode_bf_tm.cu -- one codeword per group of min(32, M/32) lanes, bit-packed (bit i of word
 // w = element 32 w + i), each lane owning one word (M = 2048: two) of every block column; identity blocks
 // connect a lane's own words, pi_k blocks read a 32-bit window lo[i] : hi[i] from shared memory.  A^-1 is
-// a 4 x 4 array of Q x Q circulants, kept as 16 first columns (<= 1 KB) in shared memory: every set bit y of
-// s XORs the window of the column rotated by y (one funnel shift) into the lane's words of p_CC.
+// a 4 x 4 array of Q x Q circulants.  Two forms of the dense product:
+//   * LUT (large batches): a nibble lookup table in shared memory ("four Russians", code_tables.h:
+//     tm_encoder_lut, 8 ... 128 KB): every nibble of s selects one pre-combined, pre-shifted row of M bits that is
+//     XORed into the codeword's words of p_CC -- one LDS + one LOP3 per word, no branches, no bit scans;
+//   * compact (a handful of codewords, where filling the table would dominate): the 16 first columns (<= 1 KB);
+//     every set bit y of s XORs the window of the column rotated by y (one funnel shift).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -32,7 +36,7 @@ using namespace tm;
 
 namespace {
 
-constexpr int kEncWarps = 8;
+constexpr int kEncWarps = 8;       // compact form; the LUT form sizes its CTA from the table (launch_enc_tm)
 
 template <class P> __host__ __device__ constexpr int n_blocks_at(int r, int c) {
     int n = 0;
@@ -62,8 +66,11 @@ __device__ __forceinline__ uint32_t load_be32(const uint8_t *p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
 
-template <int RATE, int M>
-__global__ void __launch_bounds__(32 * kEncWarps)
+template <int M> __host__ __device__ constexpr int enc_lut_words() { return 512 * (M / 32); }
+template <int M> __host__ __device__ constexpr int enc_lut_warps() { return M >= 2048 ? 24 : (M >= 512 ? 16 : 8); }
+
+template <int RATE, int M, bool LUT>
+__global__ void __launch_bounds__(32 * (LUT ? enc_lut_warps<M>() : kEncWarps))
 encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const uint8_t *__restrict__ data_all,
                  uint8_t *__restrict__ cw_all, unsigned long long batch) {
     typedef Proto<RATE> P;
@@ -76,7 +83,8 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
     constexpr int WPL = MW / LPC;                         // words per lane per block column
     constexpr int SLOTW = (KC + 2) * MW;
     constexpr int STRIDE = enc_cw_stride<P, M>();
-    constexpr int TABW = enc_tab_words<M>();
+    constexpr int TABW = LUT ? enc_lut_words<M>() : enc_tab_words<M>();
+    constexpr int kEncWarps = LUT ? enc_lut_warps<M>() : ldpc::kEncWarps;
     constexpr unsigned kFull = 0xFFFFFFFFu;
     static_assert(Q % 32 == 0 && (QW & (QW - 1)) == 0 && MW % LPC == 0, "quarters are whole words");
     // the structure the derivation above rests on (code_tables.cpp checks the same on the run-time tables)
@@ -95,9 +103,15 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
     uint32_t *lo = smem_enc + TABW + (warp * CWW + grp) * STRIDE;
     uint32_t *hi = lo + SLOTW;
 
-    for (int i = threadIdx.x; i < 16 * QW; i += blockDim.x) {
-        const int qi = i / (4 * QW);
-        tab[qi * 5 * QW + (i - qi * 4 * QW)] = ainv[i];
+    if constexpr (LUT) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ainv);
+        uint4 *dst = reinterpret_cast<uint4 *>(tab);
+        for (int i = threadIdx.x; i < TABW / 4; i += blockDim.x) dst[i] = src[i];
+    } else {
+        for (int i = threadIdx.x; i < 16 * QW; i += blockDim.x) {
+            const int qi = i / (4 * QW);
+            tab[qi * 5 * QW + (i - qi * 4 * QW)] = ainv[i];
+        }
     }
     __syncthreads();
 
@@ -194,26 +208,50 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
         uint32_t pc[WPL];
 #pragma unroll
         for (int wi = 0; wi < WPL; wi++) pc[wi] = 0;
+        if constexpr (LUT) {
 #pragma unroll
-        for (int wj = 0; wj < WPL; wj++) {
+            for (int wj = 0; wj < WPL; wj++) {
 #pragma unroll 2
-            for (int l = 0; l < LPC; l++) {
-                uint32_t D = __shfl_sync(kFull, sv[wj], grp * LPC + l);
-                const int j = l + wj * LPC, qj = j / QW, wq = j % QW;
-                uint32_t xl[WPL], xh[WPL];
+                for (int l = 0; l < LPC; l++) {
+                    const uint32_t D = __shfl_sync(kFull, sv[wj], grp * LPC + l);
+                    const int j = l + wj * LPC, qj = j / QW, wq = j % QW;
+                    const uint32_t *rows = tab + qj * (8 * 16 * MW);
+                    int idx[WPL];
 #pragma unroll
-                for (int wi = 0; wi < WPL; wi++) {
-                    const int w = wl + wi * LPC, qi = w / QW, wx = w % QW;
-                    const int w0 = (wx - wq) & (QW - 1);
-                    const uint32_t *col = tab + qi * 5 * QW + qj * QW;
-                    xh[wi] = col[w0];
-                    xl[wi] = col[(w0 - 1) & (QW - 1)];
+                    for (int wi = 0; wi < WPL; wi++) {
+                        const int w = wl + wi * LPC;
+                        idx[wi] = (w & ~(QW - 1)) | ((w - wq) & (QW - 1));
+                    }
+#pragma unroll
+                    for (int nib = 0; nib < 8; nib++) {
+                        const uint32_t *row = rows + (nib * 16 + ((D >> (4 * nib)) & 15u)) * MW;
+#pragma unroll
+                        for (int wi = 0; wi < WPL; wi++) pc[wi] ^= row[idx[wi]];
+                    }
                 }
-                while (D) {
-                    const int o = __ffs((int)D) - 1;
-                    D &= D - 1;
-#pragma unroll
-                    for (int wi = 0; wi < WPL; wi++) pc[wi] ^= __funnelshift_l(xl[wi], xh[wi], o);
+            }
+        } else {
+    #pragma unroll
+            for (int wj = 0; wj < WPL; wj++) {
+    #pragma unroll 2
+                for (int l = 0; l < LPC; l++) {
+                    uint32_t D = __shfl_sync(kFull, sv[wj], grp * LPC + l);
+                    const int j = l + wj * LPC, qj = j / QW, wq = j % QW;
+                    uint32_t xl[WPL], xh[WPL];
+    #pragma unroll
+                    for (int wi = 0; wi < WPL; wi++) {
+                        const int w = wl + wi * LPC, qi = w / QW, wx = w % QW;
+                        const int w0 = (wx - wq) & (QW - 1);
+                        const uint32_t *col = tab + qi * 5 * QW + qj * QW;
+                        xh[wi] = col[w0];
+                        xl[wi] = col[(w0 - 1) & (QW - 1)];
+                    }
+                    while (D) {
+                        const int o = __ffs((int)D) - 1;
+                        D &= D - 1;
+    #pragma unroll
+                        for (int wi = 0; wi < WPL; wi++) pc[wi] ^= __funnelshift_l(xl[wi], xh[wi], o);
+                    }
                 }
             }
         }
@@ -251,33 +289,49 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
     }
 }
 
-template <int RATE, int M>
-cudaError_t launch_enc_tm(DeviceCtx &ctx, const CodeInfo &c, const DeviceCode &dc, const uint8_t *data,
-                          uint8_t *codewords, size_t batch, cudaStream_t stream) {
+template <int RATE, int M, bool LUT>
+cudaError_t launch_enc_tm_form(DeviceCtx &ctx, const CodeInfo &c, const DeviceCode &dc, const uint8_t *data,
+                               uint8_t *codewords, size_t batch, cudaStream_t stream) {
     typedef Proto<RATE> P;
     const TmParams prm = make_params<RATE>(c);
     constexpr int MW = M / 32, CWW = MW < 32 ? 32 / MW : 1;
-    const size_t smem = ((size_t)enc_tab_words<M>() + (size_t)kEncWarps * CWW * enc_cw_stride<P, M>()) * sizeof(uint32_t);
-    auto kern = encode_tm_kernel<RATE, M>;
+    constexpr int warps = LUT ? enc_lut_warps<M>() : kEncWarps;
+    constexpr int tabw = LUT ? enc_lut_words<M>() : enc_tab_words<M>();
+    const size_t smem = ((size_t)tabw + (size_t)warps * CWW * enc_cw_stride<P, M>()) * sizeof(uint32_t);
+    auto kern = encode_tm_kernel<RATE, M, LUT>;
     static bool configured[16] = {};
     static int per_sm_cached[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kEncWarps, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem);
         if (e != cudaSuccess) return e;
         per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
         configured[ctx.device & 15] = true;
     }
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
     const unsigned long long groups = (batch + CWW - 1) / CWW;
-    const unsigned long long need = (groups + kEncWarps - 1) / kEncWarps;
+    const unsigned long long need = (groups + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid == 0) grid = 1;
-    kern<<<(unsigned)grid, 32 * kEncWarps, smem, stream>>>(prm, dc.enc_ainv, data, codewords, (unsigned long long)batch);
+    kern<<<(unsigned)grid, 32 * warps, smem, stream>>>(prm, LUT ? dc.enc_lut : dc.enc_ainv, data, codewords,
+                                                       (unsigned long long)batch);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int RATE, int M>
+cudaError_t launch_enc_tm(DeviceCtx &ctx, const CodeInfo &c, const DeviceCode &dc, const uint8_t *data,
+                          uint8_t *codewords, size_t batch, cudaStream_t stream) {
+    // The LUT form fills 8 ... 128 KB of shared memory per CTA before the first codeword; it pays once every warp
+    // of the grid has a few codeword groups to encode.  LABRADOR_LDPC_ENC_TM_FORM = 1 (compact) / 2 (LUT) forces one.
+    static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TM_FORM"); return e ? atoi(e) : 0; }();
+    constexpr int MW = M / 32, CWW = MW < 32 ? 32 / MW : 1;
+    const size_t groups = (batch + CWW - 1) / CWW;
+    const bool lut = forced ? forced == 2 : groups >= (size_t)ctx.sm_count * enc_lut_warps<M>() * 2;
+    if (lut && dc.enc_lut) return launch_enc_tm_form<RATE, M, true>(ctx, c, dc, data, codewords, batch, stream);
+    return launch_enc_tm_form<RATE, M, false>(ctx, c, dc, data, codewords, batch, stream);
 }
 
 }  // namespace

@@ -173,14 +173,14 @@ def test_encode_kat_and_random(ldpc, oracle, kats, code):
         assert np.array_equal(c.copy_encode_batch(d[:b]), want[:b]), b
 
 
-@pytest.mark.parametrize("code", [3, 5, 6, 8])
+@pytest.mark.parametrize("code", [3, 4, 5, 6, 7, 8])
 def test_encode_large_batch_and_unaligned(ldpc, oracle, code):
-    """Grid-stride path of the encoders (more codeword groups than resident warps) and byte-granular
-    pointers (plain-load path), against the oracle."""
+    """Large batches take the lookup-table form of the TM encoder (encode_tm.cu), small ones the compact
+    form; also byte-granular pointers (plain-load path).  All against the oracle."""
     import torch
     c = ldpc.LDPCCode(code)
     kb, nb = c.k() // 8, c.n() // 8
-    batch = 40000 if code in (3, 5) else 12001
+    batch = 40000 if code in (3, 4, 5) else 12001
     rng = np.random.default_rng(100 + code)
     d = rng.integers(0, 256, (batch, kb), dtype=np.uint8)
     want = oracle.copy_encode_batch(code, d, nthreads=os.cpu_count() or 1)
