@@ -206,21 +206,21 @@ bool tm_encoder_lut(int code, std::vector<uint32_t> &lut) {
     if (!tm_encoder_table(code, col)) return false;
     const int M = code_info(code)->m, Q = M / 4, QW = Q / 32, MW = M / 32;
     lut.assign((size_t)512 * MW, 0);
+    auto row = [&](int v, int qj, int nib) { return &lut[((size_t)v * 32 + qj * 8 + nib) * MW]; };
     // single-bit rows first (v = 1 << e), the rest are XORs of those
     for (int qj = 0; qj < 4; qj++)
         for (int nib = 0; nib < 8; nib++) {
-            uint32_t *rows = &lut[(size_t)(qj * 8 + nib) * 16 * MW];
             for (int e = 0; e < 4; e++)
                 for (int qi = 0; qi < 4; qi++)
                     for (int x = 0; x < Q; x++) {
                         const int z = ((x - 4 * nib - e) % Q + Q) % Q;
                         if ((col[(size_t)(qi * 4 + qj) * QW + (z >> 5)] >> (z & 31)) & 1)
-                            rows[(size_t)(1 << e) * MW + qi * QW + (x >> 5)] |= 1u << (x & 31);
+                            row(1 << e, qj, nib)[qi * QW + (x >> 5)] |= 1u << (x & 31);
                     }
             for (int v = 3; v < 16; v++) {
                 if ((v & (v - 1)) == 0) continue;
                 const int low = v & -v;
-                for (int w = 0; w < MW; w++) rows[(size_t)v * MW + w] = rows[(size_t)(v ^ low) * MW + w] ^ rows[(size_t)low * MW + w];
+                for (int w = 0; w < MW; w++) row(v, qj, nib)[w] = row(v ^ low, qj, nib)[w] ^ row(low, qj, nib)[w];
             }
         }
     return true;

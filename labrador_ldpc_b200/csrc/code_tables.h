@@ -82,7 +82,7 @@ bool tm_encoder_table(int code, std::vector<uint32_t> &out);
 // The same A^-1 as a nibble lookup table ("four Russians"): for every source quarter qj, nibble position
 // nib (0..7) inside a 32-bit word of s and nibble value v, the XOR of the (up to four) rotated columns those
 // bits select, for word offset 0:
-//     lut[((qj * 8 + nib) * 16 + v) * (M / 32) + qi * (Q / 32) + w], bit t
+//     lut[((v * 4 + qj) * 8 + nib) * (M / 32) + qi * (Q / 32) + w], bit t
 //         = XOR over bits e of v of  A^-1 [qi * Q + (32 w + t - 4 nib - e) mod Q] [qj * Q]
 // A word of s at in-quarter word index wq then contributes lut[..][(w - wq) mod (Q/32)] to word w of quarter qi
 // of the product.  512 rows of M bits: 8 KB (M = 128) ... 128 KB (M = 2048).

@@ -66,13 +66,22 @@ __device__ __forceinline__ uint32_t load_be32(const uint8_t *p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
 
-template <int M> __host__ __device__ constexpr int enc_lut_words() { return 512 * (M / 32); }
+template <int IMM> __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+
+// words between the rows of consecutive nibble values in shared memory: codes with several codewords per warp get
+// M/32 words of padding so that different values (different codewords of the warp) fall into different banks
+template <int M> __host__ __device__ constexpr int enc_lut_vstride() { return 32 * (M / 32) + (M / 32 < 32 ? M / 32 : 0); }
+template <int M> __host__ __device__ constexpr int enc_lut_words() { return 16 * enc_lut_vstride<M>(); }
 template <int M> __host__ __device__ constexpr int enc_lut_warps() { return M >= 2048 ? 24 : (M >= 512 ? 16 : 8); }
 
 template <int RATE, int M, bool LUT>
 __global__ void __launch_bounds__(32 * (LUT ? enc_lut_warps<M>() : kEncWarps))
 encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const uint8_t *__restrict__ data_all,
-                 uint8_t *__restrict__ cw_all, unsigned long long batch) {
+                 uint8_t *__restrict__ cw_all, unsigned long long batch, const uint32_t vs_lo, const uint32_t vs_hi) {
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL;
     constexpr int KC = NCOL - 3, CA = NCOL - 3, CB = NCOL - 2, CC = NCOL - 1;
@@ -106,7 +115,8 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
     if constexpr (LUT) {
         const uint4 *src = reinterpret_cast<const uint4 *>(ainv);
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
-        for (int i = threadIdx.x; i < TABW / 4; i += blockDim.x) dst[i] = src[i];
+        constexpr int ROW4 = 32 * MW / 4, VS4 = enc_lut_vstride<M>() / 4;       // per nibble value, in uint4
+        for (int i = threadIdx.x; i < 16 * ROW4; i += blockDim.x) dst[(i / ROW4) * VS4 + i % ROW4] = src[i];
     } else {
         for (int i = threadIdx.x; i < 16 * QW; i += blockDim.x) {
             const int qi = i / (4 * QW);
@@ -209,25 +219,28 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
 #pragma unroll
         for (int wi = 0; wi < WPL; wi++) pc[wi] = 0;
         if constexpr (LUT) {
+            // Row of the table for (nibble value v, source quarter qj, nibble position nib): byte offset
+            // v * VS + (qj * 8 + nib) * 4 MW (VS = enc_lut_vstride words).  v * VS comes from one LOP3 (the nibble in place inside its byte) and
+            // one IMAD whose multiplier is a kernel parameter (keeps it on the FMA pipe); the rest is an immediate.
+            const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(tab);
 #pragma unroll
             for (int wj = 0; wj < WPL; wj++) {
 #pragma unroll 2
                 for (int l = 0; l < LPC; l++) {
                     const uint32_t D = __shfl_sync(kFull, sv[wj], grp * LPC + l);
                     const int j = l + wj * LPC, qj = j / QW, wq = j % QW;
-                    const uint32_t *rows = tab + qj * (8 * 16 * MW);
-                    int idx[WPL];
-#pragma unroll
-                    for (int wi = 0; wi < WPL; wi++) {
-                        const int w = wl + wi * LPC;
-                        idx[wi] = (w & ~(QW - 1)) | ((w - wq) & (QW - 1));
-                    }
-#pragma unroll
-                    for (int nib = 0; nib < 8; nib++) {
-                        const uint32_t *row = rows + (nib * 16 + ((D >> (4 * nib)) & 15u)) * MW;
-#pragma unroll
-                        for (int wi = 0; wi < WPL; wi++) pc[wi] ^= row[idx[wi]];
-                    }
+                    // this lane's first word inside a row; its other words follow LPC words apart
+                    const uint32_t a0 = tab_sa + (uint32_t)((qj * 8 * MW + ((wl & ~(QW - 1)) | ((wl - wq) & (QW - 1)))) * 4);
+                    static_for<0, 4>([&](auto bi) {
+                        constexpr int b = decltype(bi)::value;
+                        const uint32_t Db = __byte_perm(D, 0, 0x4440 + b);
+                        const uint32_t r0 = (Db & 0x0Fu) * vs_lo + a0;          // vs_lo = VS, vs_hi = VS / 16
+                        const uint32_t r1 = (Db & 0xF0u) * vs_hi + a0;
+                        static_for<0, WPL>([&](auto wii) {
+                            constexpr int wi = decltype(wii)::value;
+                            pc[wi] ^= lds_u32<(2 * b) * MW * 4 + wi * LPC * 4>(r0) ^ lds_u32<(2 * b + 1) * MW * 4 + wi * LPC * 4>(r1);
+                        });
+                    });
                 }
             }
         } else {
@@ -316,7 +329,7 @@ cudaError_t launch_enc_tm_form(DeviceCtx &ctx, const CodeInfo &c, const DeviceCo
     if (grid > need) grid = need;
     if (grid == 0) grid = 1;
     kern<<<(unsigned)grid, 32 * warps, smem, stream>>>(prm, LUT ? dc.enc_lut : dc.enc_ainv, data, codewords,
-                                                       (unsigned long long)batch);
+                                                       (unsigned long long)batch, enc_lut_vstride<M>() * 4u, enc_lut_vstride<M>() * 4u / 16u);
     count_launch();
     return cudaGetLastError();
 }
