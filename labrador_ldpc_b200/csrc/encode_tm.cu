@@ -153,12 +153,28 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
     const unsigned long long in_stride = data_all ? (unsigned long long)(KC * MW * 4) : (unsigned long long)((KC + 2) * MW * 4);
     const uint8_t *in_base = data_all ? data_all : cw_all;
 
-    for (unsigned long long g = (unsigned long long)blockIdx.x * kEncWarps + warp; g < n_groups;
-         g += (unsigned long long)gridDim.x * kEncWarps) {
+    // raw (little-endian) data words of codeword group g; the next group's are fetched while this one is encoded
+    auto fetch = [&](unsigned long long g, uint32_t (&raw)[KC][WPL]) {
+        const unsigned long long first = g * CWW, frame = first + grp;
+        const uint8_t *in = in_base + (frame < batch ? frame : first) * in_stride;
+#pragma unroll
+        for (int wi = 0; wi < WPL; wi++)
+#pragma unroll
+            for (int c = 0; c < KC; c++) {
+                const int iw = c * MW + wl + wi * LPC;
+                if (aligned) raw[c][wi] = reinterpret_cast<const uint32_t *>(in)[iw];
+                else raw[c][wi] = __byte_perm(load_be32(in + 4 * iw), 0, 0x0123);
+            }
+    };
+    const unsigned long long g_step = (unsigned long long)gridDim.x * kEncWarps;
+    unsigned long long g = (unsigned long long)blockIdx.x * kEncWarps + warp;
+    uint32_t nxt[KC][WPL];
+    if (g < n_groups) fetch(g, nxt);
+
+    for (; g < n_groups; g += g_step) {
         const unsigned long long first = g * CWW;
         const unsigned long long frame = first + grp;
         const bool live = frame < batch;
-        const uint8_t *in = in_base + (live ? frame : first) * in_stride;
         uint8_t *cw = cw_all + (live ? frame : first) * (unsigned long long)((KC + 2) * MW * 4);
 
         // data words (bit-reversed: bit i of word w = element 32 w + i); copy_encode also writes them out
@@ -169,22 +185,20 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
 #pragma unroll
             for (int c = 0; c < KC; c++) {
                 const int iw = c * MW + w;
-                uint32_t be;
-                if (aligned) {
-                    const uint32_t raw = reinterpret_cast<const uint32_t *>(in)[iw];
-                    if (data_all && live) reinterpret_cast<uint32_t *>(cw)[iw] = raw;
-                    be = __byte_perm(raw, 0, 0x0123);
-                } else {
-                    be = load_be32(in + 4 * iw);
-                    if (data_all && live) {
-                        cw[4 * iw + 0] = (uint8_t)(be >> 24); cw[4 * iw + 1] = (uint8_t)(be >> 16);
-                        cw[4 * iw + 2] = (uint8_t)(be >> 8);  cw[4 * iw + 3] = (uint8_t)be;
+                const uint32_t raw = nxt[c][wi];
+                if (data_all && live) {
+                    if (aligned) {
+                        reinterpret_cast<uint32_t *>(cw)[iw] = raw;
+                    } else {
+                        cw[4 * iw + 0] = (uint8_t)raw; cw[4 * iw + 1] = (uint8_t)(raw >> 8);
+                        cw[4 * iw + 2] = (uint8_t)(raw >> 16);  cw[4 * iw + 3] = (uint8_t)(raw >> 24);
                     }
                 }
-                dw[c][wi] = __brev(be);
+                dw[c][wi] = __brev(__byte_perm(raw, 0, 0x0123));
                 store_word(c * MW, w, dw[c][wi]);
             }
         }
+        if (g + g_step < n_groups) fetch(g + g_step, nxt);
         __syncwarp();
 
         // t1 / t2: data terms of check rows 1 and 2
