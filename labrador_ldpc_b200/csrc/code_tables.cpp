@@ -226,4 +226,32 @@ bool tm_encoder_lut(int code, std::vector<uint32_t> &lut) {
     return true;
 }
 
+bool tc_encoder_lut(int code, int group_bits, std::vector<uint32_t> &lut) {
+    lut.clear();
+    const CodeInfo *ci = code_info(code);
+    if (!ci || ci->p != 0 || (group_bits != 4 && group_bits != 8)) return false;
+    const CodeInfo &c = *ci;
+    const int r = c.n - c.k, PW = r / 32, W64 = r / 64, nv = 1 << group_bits, groups = c.k / group_bits;
+    // parity row of one data bit, as memory-order words
+    std::vector<uint32_t> rows((size_t)c.k * PW, 0);
+    for (int i = 0; i < c.k; i++) {
+        const int crow = i / c.b, o = i % c.b;
+        for (int j = 0; j < r; j++) {
+            const int src = (j / c.b) * c.b + ((j % c.b) - o + c.b) % c.b;
+            if ((c.gen[(size_t)crow * W64 + src / 64] >> (63 - src % 64)) & 1)
+                rows[(size_t)i * PW + j / 32] |= 1u << (8 * ((j / 8) % 4) + 7 - j % 8);
+        }
+    }
+    lut.assign((size_t)groups * nv * PW, 0);
+    for (int g = 0; g < groups; g++)
+        for (int v = 1; v < nv; v++) {
+            const int low = v & -v, e = __builtin_ctz(low);
+            // bit e of the group value is data bit (first bit of the group) + group_bits - 1 - e
+            const int bit = g * group_bits + group_bits - 1 - e;
+            for (int w = 0; w < PW; w++)
+                lut[((size_t)g * nv + v) * PW + w] = lut[((size_t)g * nv + (v ^ low)) * PW + w] ^ rows[(size_t)bit * PW + w];
+        }
+    return true;
+}
+
 }  // namespace ldpc

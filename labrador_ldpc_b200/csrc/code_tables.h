@@ -88,4 +88,12 @@ bool tm_encoder_table(int code, std::vector<uint32_t> &out);
 // of the product.  512 rows of M bits: 8 KB (M = 128) ... 128 KB (M = 2048).
 bool tm_encoder_lut(int code, std::vector<uint32_t> &lut);
 
+// Lookup table of the TC-code encoder (encode.cu: encode_tc_lut_kernel): the parity contribution of every value of
+// every group of `group_bits` (4 or 8) consecutive data bits, i.e. the XOR of the generator rows those bits select
+// (reference src/encoder.rs:42-82: the row of data bit crow*b + o is compact row crow with every b-bit block rotated
+// right by o).  Data bytes are taken as they lie in memory (MSB = lowest bit index); a row is (n-k)/32 words holding
+// the parity bytes in memory order (little-endian words), so it can be XORed and stored without any byte swapping:
+//     lut[(g * 2^group_bits + v) * (n-k)/32 + w],   g = group index (byte j, or nibble 2j = high / 2j+1 = low half)
+bool tc_encoder_lut(int code, int group_bits, std::vector<uint32_t> &lut);
+
 }  // namespace ldpc

@@ -15,6 +15,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 #include "runtime.h"
 
@@ -135,6 +137,128 @@ __global__ void encode_kernel(const DeviceCode code, const uint8_t *__restrict__
     }
 }
 
+
+// ---- TC codes, large batches: one codeword per thread over a lookup table ---------------------------------
+// A TC codeword is 16 / 32 / 64 bytes.  The parity contribution of every value of every data byte (TC128, TC256:
+// 16 / 64 KB) or nibble (TC512: 32 KB) is precomputed (code_tables.h: tc_encoder_lut) in memory byte order, so a
+// thread loads its data words, XORs k/8 (k/4) table rows selected by the data bytes and stores the codeword:
+// no bit scans, no rotations, no byte swaps, no synchronisation.  KW = k/32 = (n-k)/32 words; GB = bits per group.
+template <int KW, int GB>
+__global__ void __launch_bounds__(512, 2)
+encode_tc_lut_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restrict__ data_all,
+                     uint8_t *__restrict__ cw_all, unsigned long long batch, const uint32_t row_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NV = 1 << GB, GROUPS = KW * 32 / GB;
+    constexpr int LUTW = GROUPS * NV * KW;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(lut_g);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < LUTW / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(smem);
+    typedef typename std::conditional<KW == 2, uint2, uint4>::type Vec;      // widest vector that divides a frame half
+    constexpr int VW = sizeof(Vec) / 4, NVEC = KW / VW;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(cw_all) | reinterpret_cast<uintptr_t>(data_all)) & (sizeof(Vec) - 1)) == 0;
+    const unsigned long long in_stride = data_all ? KW * 4ull : KW * 8ull;
+    const uint8_t *in_base = data_all ? data_all : cw_all;
+
+    for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < batch;
+         f += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t *in = in_base + f * in_stride;
+        uint8_t *cw = cw_all + f * (KW * 8ull);
+        uint32_t d[KW], p[KW];
+        if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < NVEC; i++) {
+                const Vec v = reinterpret_cast<const Vec *>(in)[i];
+                memcpy(&d[i * VW], &v, sizeof(Vec));
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < KW; w++)
+                d[w] = (uint32_t)in[4 * w] | ((uint32_t)in[4 * w + 1] << 8) | ((uint32_t)in[4 * w + 2] << 16) | ((uint32_t)in[4 * w + 3] << 24);
+        }
+#pragma unroll
+        for (int w = 0; w < KW; w++) p[w] = 0;
+#pragma unroll
+        for (int w = 0; w < KW; w++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t byte = __byte_perm(d[w], 0, 0x4440 + b);
+                if constexpr (GB == 8) {
+                    const uint32_t a = lut_sa + (uint32_t)((4 * w + b) * NV * KW * 4) + byte * row_bytes;
+#pragma unroll
+                    for (int i = 0; i < NVEC; i++) {
+                        Vec v;
+                        if constexpr (KW == 2) asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+                        else asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a + 16 * i));
+                        uint32_t t[VW];
+                        memcpy(t, &v, sizeof(Vec));
+#pragma unroll
+                        for (int j = 0; j < VW; j++) p[i * VW + j] ^= t[j];
+                    }
+                } else {
+                    // high nibble = group 2j, low nibble = group 2j + 1 of byte j = 4w + b
+                    const uint32_t a_hi = lut_sa + (uint32_t)(((4 * w + b) * 2) * NV * KW * 4) + (byte >> 4) * row_bytes;
+                    const uint32_t a_lo = lut_sa + (uint32_t)(((4 * w + b) * 2 + 1) * NV * KW * 4) + (byte & 15u) * row_bytes;
+#pragma unroll
+                    for (int i = 0; i < NVEC; i++) {
+                        uint4 x, y;
+                        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(a_hi + 16 * i));
+                        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(y.x), "=r"(y.y), "=r"(y.z), "=r"(y.w) : "r"(a_lo + 16 * i));
+                        p[i * 4 + 0] ^= x.x ^ y.x; p[i * 4 + 1] ^= x.y ^ y.y; p[i * 4 + 2] ^= x.z ^ y.z; p[i * 4 + 3] ^= x.w ^ y.w;
+                    }
+                }
+            }
+        }
+        if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < NVEC; i++) {
+                Vec v;
+                if (data_all) { memcpy(&v, &d[i * VW], sizeof(Vec)); reinterpret_cast<Vec *>(cw)[i] = v; }
+                memcpy(&v, &p[i * VW], sizeof(Vec));
+                reinterpret_cast<Vec *>(cw)[NVEC + i] = v;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < KW; w++) {
+                if (data_all) {
+                    cw[4 * w] = (uint8_t)d[w]; cw[4 * w + 1] = (uint8_t)(d[w] >> 8);
+                    cw[4 * w + 2] = (uint8_t)(d[w] >> 16); cw[4 * w + 3] = (uint8_t)(d[w] >> 24);
+                }
+                uint8_t *o = cw + KW * 4 + 4 * w;
+                o[0] = (uint8_t)p[w]; o[1] = (uint8_t)(p[w] >> 8); o[2] = (uint8_t)(p[w] >> 16); o[3] = (uint8_t)(p[w] >> 24);
+            }
+        }
+    }
+}
+
+template <int KW, int GB>
+cudaError_t launch_encode_tc_lut(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords,
+                                 size_t batch, cudaStream_t stream) {
+    constexpr int threads = 512;
+    const size_t smem = (size_t)(KW * 32 / GB) * (1 << GB) * KW * 4;
+    auto kern = encode_tc_lut_kernel<KW, GB>;
+    static bool configured[16] = {};
+    static int per_sm_cached[16] = {};
+    if (!configured[ctx.device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device & 15] = true;
+    }
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    const unsigned long long need = (batch + threads - 1) / threads;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, KW * 4u);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int WPT>
 cudaError_t launch_encode_wpt(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords,
                               size_t batch, cudaStream_t stream) {
@@ -171,6 +295,15 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
     if (!force_gen) {
         cudaError_t err = cudaSuccess;
         if (launch_encode_tm(ctx, code, data, codewords, batch, stream, &err)) return err;
+    }
+    // TC codes, large batches: one codeword per thread over a byte / nibble lookup table (filling the table costs
+    // 16-64 KB of L2 reads per CTA, so small batches stay on the generator kernel)
+    if (!force_gen && code < 3 && dc.enc_tc_lut && batch >= (size_t)ctx.sm_count * 1024) {
+        switch (code) {
+            case 0: return launch_encode_tc_lut<2, 8>(ctx, dc, data, codewords, batch, stream);
+            case 1: return launch_encode_tc_lut<4, 8>(ctx, dc, data, codewords, batch, stream);
+            default: return launch_encode_tc_lut<8, 4>(ctx, dc, data, codewords, batch, stream);
+        }
     }
     // words per thread: the number of circulant blocks per row (n-k)/b must be divisible by it
     static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_ENC_WPT"); return e ? atoi(e) : 0; }();

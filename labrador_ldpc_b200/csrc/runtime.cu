@@ -84,7 +84,7 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
     CUDA_TRY(cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
 
     std::vector<unsigned char> blob;
-    struct Off { size_t var_tab, chk_tab, gen, gen32, ainv, lut; bool has_ainv; };
+    struct Off { size_t var_tab, chk_tab, gen, gen32, ainv, lut, tc_lut; bool has_ainv, has_tc_lut; };
     Off offs[kNumCodes];
     for (int ci = 0; ci < kNumCodes; ci++) {
         const CodeInfo &c = *code_info(ci);
@@ -109,6 +109,9 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         std::vector<uint32_t> ainv;
         offs[ci].has_ainv = tm_encoder_table(ci, ainv);
         offs[ci].ainv = offs[ci].has_ainv ? append(ainv.data(), ainv.size() * 4) : 0;
+        std::vector<uint32_t> tc_lut;
+        offs[ci].has_tc_lut = tc_encoder_lut(ci, ci == 2 ? 4 : 8, tc_lut);
+        offs[ci].tc_lut = offs[ci].has_tc_lut ? append(tc_lut.data(), tc_lut.size() * 4) : 0;
         std::vector<uint32_t> lut;
         offs[ci].lut = (offs[ci].has_ainv && tm_encoder_lut(ci, lut)) ? append(lut.data(), lut.size() * 4) : 0;
     }
@@ -127,6 +130,7 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         d.gen = reinterpret_cast<const uint64_t *>(base + offs[ci].gen);
         d.gen32 = reinterpret_cast<const uint32_t *>(base + offs[ci].gen32);
         d.enc_ainv = offs[ci].has_ainv ? reinterpret_cast<const uint32_t *>(base + offs[ci].ainv) : nullptr;
+        d.enc_tc_lut = offs[ci].has_tc_lut ? reinterpret_cast<const uint32_t *>(base + offs[ci].tc_lut) : nullptr;
         d.enc_lut = offs[ci].has_ainv ? reinterpret_cast<const uint32_t *>(base + offs[ci].lut) : nullptr;
     }
     for (int i = 0; i < DeviceCtx::kPipe; i++)

@@ -49,6 +49,7 @@ struct DeviceCode {
     const uint64_t *gen;       // compact generator rows
     const uint32_t *gen32;     // same rows as big-endian-ordered 32-bit words
     const uint32_t *enc_ainv;  // TM codes: first columns of the circulants of A^-1 (code_tables.h: tm_encoder_table), else null
+    const uint32_t *enc_tc_lut; // TC codes: byte (TC128, TC256) / nibble (TC512) table of parity contributions, else null
     const uint32_t *enc_lut;   // TM codes: the same as a nibble lookup table (code_tables.h: tm_encoder_lut), else null
 };
 

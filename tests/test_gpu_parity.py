@@ -173,14 +173,15 @@ def test_encode_kat_and_random(ldpc, oracle, kats, code):
         assert np.array_equal(c.copy_encode_batch(d[:b]), want[:b]), b
 
 
-@pytest.mark.parametrize("code", [3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("code", CODES)
 def test_encode_large_batch_and_unaligned(ldpc, oracle, code):
-    """Large batches take the lookup-table form of the TM encoder (encode_tm.cu), small ones the compact
-    form; also byte-granular pointers (plain-load path).  All against the oracle."""
+    """Large batches take the lookup-table encoders (TM: encode_tm.cu, TC: encode_tc_lut_kernel), small ones the
+    compact TM form / the generator kernel; also byte-granular pointers (plain-load paths) and the in-place
+    form.  All against the oracle."""
     import torch
     c = ldpc.LDPCCode(code)
     kb, nb = c.k() // 8, c.n() // 8
-    batch = 40000 if code in (3, 4, 5) else 12001
+    batch = 200001 if code < 3 else (40000 if code in (3, 4, 5) else 12001)
     rng = np.random.default_rng(100 + code)
     d = rng.integers(0, 256, (batch, kb), dtype=np.uint8)
     want = oracle.copy_encode_batch(code, d, nthreads=os.cpu_count() or 1)
@@ -188,8 +189,13 @@ def test_encode_large_batch_and_unaligned(ldpc, oracle, code):
     got = c.copy_encode_batch(dev)
     torch.cuda.synchronize()
     assert np.array_equal(got.cpu().numpy(), want)
-    # unaligned device buffers (offset 1 and 2 bytes)
-    small = 67
+    inplace = torch.zeros((batch, nb), dtype=torch.uint8, device="cuda")
+    inplace[:, :kb] = dev
+    c.encode_batch(inplace)
+    torch.cuda.synchronize()
+    assert np.array_equal(inplace.cpu().numpy(), want)
+    # unaligned device buffers (offset 1 and 2 bytes); the TC table kernel only runs on large batches
+    small = batch if code < 3 else 67
     src = torch.zeros(small * kb + 8, dtype=torch.uint8, device="cuda")
     dst = torch.zeros(small * nb + 8, dtype=torch.uint8, device="cuda")
     src[1:1 + small * kb] = dev[:small].reshape(-1)
