@@ -202,12 +202,19 @@ encode_tc_lut_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restri
                     // high nibble = group 2j, low nibble = group 2j + 1 of byte j = 4w + b
                     const uint32_t a_hi = lut_sa + (uint32_t)(((4 * w + b) * 2) * NV * KW * 4) + (byte >> 4) * row_bytes;
                     const uint32_t a_lo = lut_sa + (uint32_t)(((4 * w + b) * 2 + 1) * NV * KW * 4) + (byte & 15u) * row_bytes;
+                    if constexpr (KW == 2) {
+                        uint2 x, y;
+                        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x.x), "=r"(x.y) : "r"(a_hi));
+                        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(y.x), "=r"(y.y) : "r"(a_lo));
+                        p[0] ^= x.x ^ y.x; p[1] ^= x.y ^ y.y;
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < NVEC; i++) {
-                        uint4 x, y;
-                        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(a_hi + 16 * i));
-                        asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(y.x), "=r"(y.y), "=r"(y.z), "=r"(y.w) : "r"(a_lo + 16 * i));
-                        p[i * 4 + 0] ^= x.x ^ y.x; p[i * 4 + 1] ^= x.y ^ y.y; p[i * 4 + 2] ^= x.z ^ y.z; p[i * 4 + 3] ^= x.w ^ y.w;
+                        for (int i = 0; i < NVEC; i++) {
+                            uint4 x, y;
+                            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(a_hi + 16 * i));
+                            asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(y.x), "=r"(y.y), "=r"(y.z), "=r"(y.w) : "r"(a_lo + 16 * i));
+                            p[i * 4 + 0] ^= x.x ^ y.x; p[i * 4 + 1] ^= x.y ^ y.y; p[i * 4 + 2] ^= x.z ^ y.z; p[i * 4 + 3] ^= x.w ^ y.w;
+                        }
                     }
                 }
             }
@@ -300,7 +307,7 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
     // 16-64 KB of L2 reads per CTA, so small batches stay on the generator kernel)
     if (!force_gen && code < 3 && dc.enc_tc_lut && batch >= (size_t)ctx.sm_count * 1024) {
         switch (code) {
-            case 0: return launch_encode_tc_lut<2, 8>(ctx, dc, data, codewords, batch, stream);
+            case 0: return launch_encode_tc_lut<2, kTc128GroupBits>(ctx, dc, data, codewords, batch, stream);
             case 1: return launch_encode_tc_lut<4, 8>(ctx, dc, data, codewords, batch, stream);
             default: return launch_encode_tc_lut<8, 4>(ctx, dc, data, codewords, batch, stream);
         }
