@@ -406,6 +406,14 @@ unsigned long long labrador_ldpc_kernel_launch_count(void);
 const char *labrador_ldpc_decode_ms_kernel_name(enum labrador_ldpc_code code, int llr_type);
 /* CRC-32 of the expanded edge table of `code` in reference order (src/codes/mod.rs:508-535). */
 uint32_t labrador_ldpc_edge_table_crc(enum labrador_ldpc_code code);
+/* Host-only model of the encoders (no GPU needed; used by the CPU tests).  The batched encoders do not multiply by
+ * the compact generator as EncodeInto::encode_parity does (src/encoder.rs:42-82): TM codes are encoded through the
+ * sparse parity-check matrix and one derived M x M inverse, TC codes through a table of per-byte parity
+ * contributions.  This call computes the (n-k)/8 parity bytes of one data block (k/8 bytes) both ways on the host:
+ * parity_tables from the very tables the kernels use, parity_generator by the reference's algorithm.
+ * Returns 0, or a negative error if a table could not be derived or its two forms disagree. */
+int labrador_ldpc_host_encode_model(enum labrador_ldpc_code code, const uint8_t *data, uint8_t *parity_tables,
+                                    uint8_t *parity_generator);
 
 #ifdef __cplusplus
 }

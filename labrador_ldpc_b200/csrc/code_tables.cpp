@@ -254,4 +254,108 @@ bool tc_encoder_lut(int code, int group_bits, std::vector<uint32_t> &lut) {
     return true;
 }
 
+void host_encode_generator(int code, const uint8_t *data, uint8_t *parity) {
+    const CodeInfo &c = *code_info(code);
+    const int r = c.n - c.k, W64 = r / 64;
+    for (int i = 0; i < r / 8; i++) parity[i] = 0;
+    for (int i = 0; i < c.k; i++) {
+        if (!((data[i / 8] >> (7 - i % 8)) & 1)) continue;
+        const int crow = i / c.b, o = i % c.b;
+        for (int j = 0; j < r; j++) {
+            const int src = (j / c.b) * c.b + ((j % c.b) - o + c.b) % c.b;      // row crow, blocks rotated right by o
+            if ((c.gen[(size_t)crow * W64 + src / 64] >> (63 - src % 64)) & 1) parity[j / 8] ^= (uint8_t)(0x80 >> (j % 8));
+        }
+    }
+}
+
+namespace {
+uint32_t brev32(uint32_t x) {
+    uint32_t r = 0;
+    for (int i = 0; i < 32; i++)
+        if ((x >> i) & 1) r |= 1u << (31 - i);
+    return r;
+}
+uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31)); }
+uint32_t funnel_l(uint32_t lo, uint32_t hi, unsigned s) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (s & 31)) >> 32); }
+}  // namespace
+
+bool host_encode_tables(int code, const uint8_t *data, uint8_t *parity) {
+    const CodeInfo *ci = code_info(code);
+    if (!ci) return false;
+    const CodeInfo &c = *ci;
+    if (c.p == 0) {                                          // TC codes: encode_tc_lut_kernel
+        const int GB = tc_encoder_group_bits(code), NV = 1 << GB, KW = c.k / 32;
+        std::vector<uint32_t> lut;
+        if (!tc_encoder_lut(code, GB, lut)) return false;
+        std::vector<uint32_t> p(KW, 0);
+        for (int j = 0; j < c.k / 8; j++)
+            for (int w = 0; w < KW; w++) {
+                if (GB == 8) p[w] ^= lut[((size_t)j * NV + data[j]) * KW + w];
+                else p[w] ^= lut[((size_t)(2 * j) * NV + (data[j] >> 4)) * KW + w] ^ lut[((size_t)(2 * j + 1) * NV + (data[j] & 15)) * KW + w];
+            }
+        for (int i = 0; i < (c.n - c.k) / 8; i++) parity[i] = (uint8_t)(p[i / 4] >> (8 * (i % 4)));
+        return true;
+    }
+    // TM codes: encode_tm_kernel (both forms of the dense product)
+    std::vector<uint32_t> ainv, lut;
+    if (!tm_encoder_table(code, ainv) || !tm_encoder_lut(code, lut)) return false;
+    const int M = c.m, Q = M / 4, QW = Q / 32, MW = M / 32, KC = c.cols - 3, CB = c.cols - 2, CC = c.cols - 1;
+    auto slot = [&](int col) { return col < KC ? col : (col == CB ? KC : KC + 1); };
+    std::vector<uint32_t> lo((size_t)(KC + 2) * MW), hi((size_t)(KC + 2) * MW);
+    auto store = [&](int base, int w, uint32_t v) { lo[base + w] = v; hi[base + ((w & ~(QW - 1)) | ((w - 1) & (QW - 1)))] = v; };
+    auto window = [&](const Block &b, int w) {
+        const int e0 = w * 32, qa = e0 / Q, off = e0 % Q;
+        const int qv = (b.theta + qa) & 3, s0 = (b.phi[qa] + off) & (Q - 1);
+        const int i = slot(b.col) * MW + qv * QW + (s0 >> 5);
+        return funnel_r(lo[i], hi[i], s0 & 31);
+    };
+    std::vector<uint32_t> dw((size_t)KC * MW), t1(MW), sv(MW), pc(MW, 0), pc2(MW, 0);
+    for (int col = 0; col < KC; col++)
+        for (int w = 0; w < MW; w++) {
+            const uint8_t *p = &data[4 * (col * MW + w)];
+            dw[col * MW + w] = brev32(((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]);
+            store(col * MW, w, dw[col * MW + w]);
+        }
+    for (int w = 0; w < MW; w++) {
+        uint32_t x1 = 0, x2 = 0;
+        for (int bi = 0; bi < c.n_blocks; bi++) {
+            const Block &b = c.blocks[bi];
+            if (b.col >= KC) continue;
+            const uint32_t v = b.kind == kPermutation ? window(b, w) : dw[b.col * MW + w];
+            if (b.row == 1) x1 ^= v; else x2 ^= v;
+        }
+        t1[w] = x1; sv[w] = x2;
+    }
+    for (int w = 0; w < MW; w++) store(KC * MW, w, t1[w]);
+    for (int w = 0; w < MW; w++)
+        for (int bi = 0; bi < c.n_blocks; bi++)
+            if (c.blocks[bi].col == CB && c.blocks[bi].row == 2) sv[w] ^= window(c.blocks[bi], w);
+    for (int j = 0; j < MW; j++) {
+        const int qj = j / QW, wq = j % QW;
+        for (int w = 0; w < MW; w++) {
+            const int qi = w / QW, wx = w % QW, w0 = (wx - wq) & (QW - 1);
+            const uint32_t *col = &ainv[(size_t)(qi * 4 + qj) * QW];
+            for (uint32_t D = sv[j]; D; D &= D - 1) pc[w] ^= funnel_l(col[(w0 - 1) & (QW - 1)], col[w0], __builtin_ctz(D));
+            for (int nib = 0; nib < 8; nib++)
+                pc2[w] ^= lut[((size_t)((sv[j] >> (4 * nib)) & 15) * 32 + qj * 8 + nib) * MW + ((w & ~(QW - 1)) | ((w - wq) & (QW - 1)))];
+        }
+    }
+    if (pc != pc2) return false;
+    for (int w = 0; w < MW; w++) store((KC + 1) * MW, w, pc[w]);
+    for (int w = 0; w < MW; w++) {
+        uint32_t pa = 0, pb = t1[w];
+        for (int bi = 0; bi < c.n_blocks; bi++) {
+            const Block &b = c.blocks[bi];
+            if (b.col == CC && b.row == 1) pb ^= window(b, w);
+            if (b.col == CC && b.row == 0) pa ^= b.kind == kPermutation ? window(b, w) : pc[w];
+        }
+        const uint32_t ra = brev32(pa), rb = brev32(pb);
+        for (int k = 0; k < 4; k++) {
+            parity[4 * w + k] = (uint8_t)(ra >> (24 - 8 * k));
+            parity[M / 8 + 4 * w + k] = (uint8_t)(rb >> (24 - 8 * k));
+        }
+    }
+    return true;
+}
+
 }  // namespace ldpc

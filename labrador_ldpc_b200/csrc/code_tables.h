@@ -95,5 +95,16 @@ bool tm_encoder_lut(int code, std::vector<uint32_t> &lut);
 // the parity bytes in memory order (little-endian words), so it can be XORed and stored without any byte swapping:
 //     lut[(g * 2^group_bits + v) * (n-k)/32 + w],   g = group index (byte j, or nibble 2j = high / 2j+1 = low half)
 bool tc_encoder_lut(int code, int group_bits, std::vector<uint32_t> &lut);
+// group size the table kernel is instantiated with: nibble rows for TC128 (16 rows = one sweep of the 32 banks, so a
+// load never conflicts) and TC512 (table size), byte rows for TC256
+inline int tc_encoder_group_bits(int code) { return code == 1 ? 8 : 4; }
+
+// Host-side models of the encoders, for the CPU tests (tests/test_capi_host.py): the parity bytes of one data block
+//   * host_encode_generator: by the compact generator, the reference's algorithm (src/encoder.rs:42-82);
+//   * host_encode_tables:    by the derived tables, word for word the way the kernels use them -- TM codes: windows,
+//     A^-1 as first columns (funnel shifts) AND as nibble lookup table, which must agree; TC codes: the byte / nibble
+//     table.  Returns false if a table is missing or the two TM forms disagree.
+void host_encode_generator(int code, const uint8_t *data, uint8_t *parity);
+bool host_encode_tables(int code, const uint8_t *data, uint8_t *parity);
 
 }  // namespace ldpc

@@ -53,9 +53,6 @@ struct DeviceCode {
     const uint32_t *enc_lut;   // TM codes: the same as a nibble lookup table (code_tables.h: tm_encoder_lut), else null
 };
 
-// bits per table group of the TC128 table encoder (encode.cu; 8 = byte rows, 4 = nibble rows)
-constexpr int kTc128GroupBits = 4;
-
 struct DeviceCtx {
     int device = -1;
     int sm_count = 0;

@@ -56,6 +56,37 @@ def test_edge_table_crc_goldens(ldpc, kats):
         assert ldpc.LDPCCode(code).edge_table_crc() == kats["edge_crc32"][code]
 
 
+def test_encoder_tables_against_generator_and_oracle(ldpc, kats):
+    """The derived encoder tables (TM: block-circulant inverse of the parity part of H as first columns and as
+    nibble lookup table; TC: byte / nibble table) reproduce the generator encoder and the oracle on the host,
+    for the reference's known answers (src/encoder.rs:361-527) and random data."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    oracle = pyoracle.Oracle()
+    L = ldpc.lib
+    L.labrador_ldpc_host_encode_model.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.labrador_ldpc_host_encode_model.restype = ctypes.c_int
+    names = ["TC128", "TC256", "TC512", "TM1280", "TM1536", "TM2048", "TM5120", "TM6144", "TM8192"]
+    rng = np.random.default_rng(7)
+    for code in range(9):
+        c = ldpc.LDPCCode(code)
+        kb, pb = c.k() // 8, (c.n() - c.k()) // 8
+        cases = [(np.arange(kb) % 256).astype(np.uint8), np.zeros(kb, np.uint8), np.full(kb, 0xFF, np.uint8)]
+        cases += [rng.integers(0, 256, kb, dtype=np.uint8) for _ in range(3)]
+        one = np.zeros(kb, np.uint8)
+        one[kb - 1] = 1                      # a single data bit (the last one)
+        cases.append(one)
+        for i, data in enumerate(cases):
+            pt, pg = np.zeros(pb, np.uint8), np.zeros(pb, np.uint8)
+            assert L.labrador_ldpc_host_encode_model(code, data.ctypes.data, pt.ctypes.data, pg.ctypes.data) == 0
+            want = oracle.copy_encode(code, data)[kb:]
+            assert np.array_equal(pg, want), (names[code], i, "generator model")
+            assert np.array_equal(pt, want), (names[code], i, "table model")
+            if i == 0:
+                assert pt.tolist() == kats["encode_parity"][names[code]]
+    assert L.labrador_ldpc_host_encode_model(9, cases[0].ctypes.data, pt.ctypes.data, pg.ctypes.data) < 0
+
+
 def test_header_macros_compile_and_match(kats, tmp_path):
     # compile a C program against include/labrador_ldpc.h and compare every size macro
     # (incl. the reference's misspelt _TM6140 names) with the reference's literal table
