@@ -305,7 +305,8 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
     }
     // TC codes, large batches: one codeword per thread over a byte / nibble lookup table (filling the table costs
     // 16-64 KB of L2 reads per CTA, so small batches stay on the generator kernel)
-    if (!force_gen && code < 3 && dc.enc_tc_lut && batch >= (size_t)ctx.sm_count * 1024) {
+    static const bool tc_table_always = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TC_TABLE"); return e && atoi(e) != 0; }();
+    if (!force_gen && code < 3 && dc.enc_tc_lut && (tc_table_always || batch >= (size_t)ctx.sm_count * 1024)) {
         // group sizes: code_tables.h: tc_encoder_group_bits
         switch (code) {
             case 0: return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);

@@ -36,4 +36,12 @@ for code in (0, 5):                                                             
         c.awgn_batch(cw, 0.7, 9.0, 5, 0, ty, limit=lim)
     out = np.zeros((13, c.output_len()), np.uint8); out[:, : c.n() // 8] = cw
     assert not c.count_errors_batch(out, data).any()
+for code in range(9):                                                            # encoders, ragged batch, in place too
+    c = L.LDPCCode(code)                                                         # (LABRADOR_LDPC_ENC_TM_FORM=2 LABRADOR_LDPC_ENC_TC_TABLE=1: table forms)
+    d = np.random.default_rng(code).integers(0, 256, (37, c.k() // 8), dtype=np.uint8)
+    want = o.copy_encode_batch(code, d, nthreads=4)
+    assert np.array_equal(c.copy_encode_batch(d), want)
+    ip = np.zeros_like(want); ip[:, : c.k() // 8] = d
+    c.encode_batch(ip)
+    assert np.array_equal(ip, want)
 print("sanitize_small OK")
