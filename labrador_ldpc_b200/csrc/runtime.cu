@@ -33,6 +33,10 @@ bool launch_decode_ms_tc(DeviceCtx &ctx, int code, int llr_type, const void *llr
                          size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err,
                          const Front &front);
 bool has_decode_ms_tc(int code);
+// decode_ms_tc_x2.cu: i8 on the TC codes, two codewords per register
+bool launch_decode_ms_tc_x2(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch, size_t max_iters,
+                            uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err, const Front &front);
+bool tc_x2_enabled();
 
 namespace {
 
@@ -268,6 +272,9 @@ cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void 
         if (launch_decode_ms_tm_wide(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err,
                                      front))
             return err;
+        if (llr_type == kI8 &&
+            launch_decode_ms_tc_x2(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err, front))
+            return err;
         if (launch_decode_ms_tc(ctx, code, llr_type, llrs, output, batch, max_iters, success, iters, stream, &err, front))
             return err;
     }
@@ -287,6 +294,7 @@ const char *decode_ms_kernel_name(int code, int llr_type) {
         static const char *wide[kNumLlrTypes] = {"ms_tm_wide<i8>", "ms_tm_wide<i16>", "ms_tm_wide<i32>", "ms_tm_wide<f32>", "ms_tm_wide<f64>"};
         return wide[llr_type];
     }
+    if (has_decode_ms_tc(code) && !force_generic() && llr_type == kI8 && tc_x2_enabled()) return "ms_tc_x2<i8>";
     if (has_decode_ms_tc(code) && !force_generic() && llr_type >= 0 && llr_type < kNumLlrTypes) {
         static const char *tc[kNumLlrTypes] = {"ms_tc_warp<i8>", "ms_tc_warp<i16>", "ms_tc_warp<i32>", "ms_tc_warp<f32>", "ms_tc_warp<f64>"};
         return tc[llr_type];

@@ -585,7 +585,7 @@ def test_specialised_kernel_dispatch(ldpc):
         pytest.skip("generic forced")
     for (code, ty), name in names.items():
         if code < 3:
-            assert name == "ms_tc_warp<%s>" % ty
+            assert name == ("ms_tc_x2<i8>" if ty == "i8" else "ms_tc_warp<%s>" % ty)
         elif code >= 4 and ty == "i8":
             assert name == "ms_tm_s16x2<i8>"
         else:
