@@ -238,6 +238,26 @@ def test_decode_ms_i8_awgn_exact(ldpc, oracle, code):
     assert 0 < want[1].sum(), "test vector should contain successes"
 
 
+@pytest.mark.parametrize("code", [0, 1, 2])
+def test_tc_packed_pair_kernel_streams(ldpc, oracle, code):
+    """decode_ms_tc_x2.cu: two codewords share every register and each 16-bit half runs its own stream of
+    frames.  Odd batches (one half runs dry first), a mix of frames that converge at once, slowly and never
+    (re-initialisation of one half while its partner is mid-decode), tight iteration caps, and the A/B kernel."""
+    c = ldpc.LDPCCode(code)
+    assert c.decode_ms_kernel_name("i8") == "ms_tc_x2<i8>"
+    rng = np.random.default_rng(900 + code)
+    parts = [make_frames(oracle, code, 301, eb, seed=910 + 7 * code + i, ty="i8")[2] for i, eb in enumerate((0.0, 2.5, 6.0))]
+    llrs = np.concatenate(parts)
+    llrs = llrs[rng.permutation(llrs.shape[0])]                  # 903 frames: hopeless, marginal and clean ones interleaved
+    for batch, iters in ((903, 100), (2, 100), (3, 7), (257, 1), (64, 2), (5, 100)):
+        want = oracle.decode_ms_batch(code, llrs[:batch], iters, nthreads=8)
+        got = c.decode_ms_batch(llrs[:batch], iters)
+        assert_exact(got, want, "%s batch %d iters %d" % (NAMES[code], batch, iters))
+    want = oracle.decode_ms_batch(code, llrs, 100, nthreads=8)
+    assert 0 < want[1].sum() < llrs.shape[0], "needs both successes and failures"
+    assert len(set(want[2].tolist())) > 5, "needs a spread of iteration counts"
+
+
 @pytest.mark.parametrize("code", [0, 2, 3, 5, 8])
 @pytest.mark.parametrize("ty", ["i16", "i32"])
 def test_decode_ms_wide_int_awgn_exact(ldpc, oracle, code, ty):
