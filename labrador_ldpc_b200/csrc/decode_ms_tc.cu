@@ -8,7 +8,8 @@
 // A group of G = min(M, 32) lanes decodes one codeword: lane s owns element s (and s+32 for M = 64)
 // of every prototype column (variable side) and every prototype row (check side).  TC128 packs two
 // codewords into one warp.  Messages live in a per-warp slice of shared memory in check order
-// (the variable side reads/writes element (j - shift) mod M of the block), the two phases of an
+// (the variable side reads/writes element (j - shift) mod M of the block; the rotations are compile-time constants, so
+// equal ones share their index arithmetic), the two phases of an
 // iteration are separated by __syncwarp() only -- no CTA barrier anywhere -- and every lane group
 // claims its next codeword from an atomic counter the moment its current one converges or gives up,
 // so a slow codeword stalls neither another warp nor the other group of its own warp.
@@ -38,7 +39,7 @@ template <int M> __host__ __device__ constexpr int tc_msg_stride() { return M < 
 
 template <int M, class T, int FRONT = kFrontNone>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
-decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
+decode_ms_tc_kernel(const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
                     uint8_t *__restrict__ out_all,
                     unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                     uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
@@ -132,7 +133,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                         tc_static_for<0, 32>([&](auto bi) {
                             constexpr int b = decltype(bi)::value;
                             if constexpr (tc_blk(b).col == c) {
-                                const int i = (j - (int)prm.shift[b]) & (M - 1);
+                                const int i = (j - tc_const_shift<M>(b)) & (M - 1);
                                 const CT u = (CT)msg[b * M + i];
                                 ub[tc_pos_in_col(b)] = u;
                                 if constexpr (kBiased) va = (CT)__viaddmin_s32_relu((int)va, (int)u, 2 * kB - 1);
@@ -145,7 +146,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                         tc_static_for<0, 32>([&](auto bi) {
                             constexpr int b = decltype(bi)::value;
                             if constexpr (tc_blk(b).col == c) {
-                                const int i = (j - (int)prm.shift[b]) & (M - 1);
+                                const int i = (j - tc_const_shift<M>(b)) & (M - 1);
                                 if constexpr (kBiased)
                                     msg[b * M + i] = (ST)__viaddmin_s32_relu(van, (int)ub[tc_pos_in_col(b)], 2 * kMaxV);
                                 else
@@ -180,7 +181,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                                 ck[k] = cor;
                                 a[k] = __usad(cor, (uint32_t)kMaxV, 0u);                 // |v|
                                 sx ^= cor;
-                                par ^= hbv[tc_blk(b).col * M + ((i + (int)prm.shift[b]) & (M - 1))];   // :445-447
+                                par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];   // :445-447
                             });
                             par_any |= par != 0;
                             min_excluding_self_u32<8, 8>(a, mu);                         // :391-395
@@ -206,7 +207,7 @@ decode_ms_tc_kernel(const TcParams prm, const typename FrontSrc<FRONT, T>::type 
                             a[k] = A::abs(v);
                             sg[k] = A::hard_bit(v);
                             stot ^= sg[k];
-                            par ^= hbv[tc_blk(b).col * M + ((i + (int)prm.shift[b]) & (M - 1))];   // :445-447
+                            par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];   // :445-447
                         });
                         par_any |= par != 0;
                         suf[7] = a[7];
@@ -261,8 +262,6 @@ cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
                       const Front &front = Front()) {
     constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
-    TcParams prm{};
-    for (int b = 0; b < 32; b++) prm.shift[b] = (uint8_t)c.blocks[b].shift;
     const size_t warp_bytes = ((sizeof(typename MsgStore<T>::type) * CWW * tc_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kWarpsPerCta;
     auto kern = decode_ms_tc_kernel<M, T, FRONT>;
@@ -285,7 +284,7 @@ cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kWarpsPerCta, smem, stream>>>(
-        prm, static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs), output, (unsigned long long)batch, mi, success,
+        static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs), output, (unsigned long long)batch, mi, success,
         iters, counter, front.scale, front.limit);
     count_launch();
     return cudaGetLastError();
@@ -324,6 +323,9 @@ bool launch_decode_ms_tc(DeviceCtx &ctx, int code, int llr_type, const void *llr
     if (code < 0 || code > 2) return false;
     const CodeInfo &c = *code_info(code);
     if (!tc_structure_matches(c)) return false;
+    // the kernels carry the rotations as compile-time constants (tc_common.cuh)
+    if (!(c.m == 16 ? tc_const_shifts_match<16>(c) : c.m == 32 ? tc_const_shifts_match<32>(c) : tc_const_shifts_match<64>(c)))
+        return false;
     switch (c.m) {
         case 16: return tc_dispatch<16>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 32: return tc_dispatch<32>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);

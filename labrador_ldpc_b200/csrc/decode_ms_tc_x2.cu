@@ -58,7 +58,7 @@ __device__ __forceinline__ void min_excluding_self8(const uint32_t (&a)[8], uint
 
 template <int M, int FRONT>
 __global__ void __launch_bounds__(32 * kX2Warps)
-decode_ms_tc_i8x2_kernel(const TcParams prm, const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
+decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
                          uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
                          uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
                          unsigned long long *__restrict__ counter, const float fscale, const float flimit) {
@@ -137,7 +137,7 @@ decode_ms_tc_i8x2_kernel(const TcParams prm, const typename FrontSrc<FRONT, int8
                 tc_static_for<0, 32>([&](auto bi) {
                     constexpr int b = decltype(bi)::value;
                     if constexpr (tc_blk(b).col == c) {
-                        const int i = (j - (int)prm.shift[b]) & (M - 1);
+                        const int i = (j - tc_const_shift<M>(b)) & (M - 1);
                         const uint32_t u = msg[b * M + i];
                         ub[tc_pos_in_col(b)] = u;
                         va = __viaddmin_s16x2_relu(va, u, 0x00ff00ffu);             // saturating_add, ascending idx (:408)
@@ -150,7 +150,7 @@ decode_ms_tc_i8x2_kernel(const TcParams prm, const typename FrontSrc<FRONT, int8
                 tc_static_for<0, 32>([&](auto bi) {
                     constexpr int b = decltype(bi)::value;
                     if constexpr (tc_blk(b).col == c) {
-                        const int i = (j - (int)prm.shift[b]) & (M - 1);
+                        const int i = (j - tc_const_shift<M>(b)) & (M - 1);
                         msg[b * M + i] = __viaddmin_s16x2_relu(van, ub[tc_pos_in_col(b)], 0x00fe00feu);   // C = 127 - clamp(va - u)
                     }
                 });
@@ -179,7 +179,7 @@ decode_ms_tc_i8x2_kernel(const TcParams prm, const typename FrontSrc<FRONT, int8
                     ck[k] = cor;
                     a[k] = __vabsdiffu4(cor, 0x007f007fu);                          // |v|
                     sx ^= cor;                                                      // bit 7: product of signs
-                    par ^= hbv[tc_blk(b).col * M + ((i + (int)prm.shift[b]) & (M - 1))];
+                    par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];
                 });
                 par_any |= par;
                 min_excluding_self8(a, mu);
@@ -227,8 +227,6 @@ template <int M, int FRONT>
 cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, const Front &front) {
     constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
-    TcParams prm{};
-    for (int b = 0; b < 32; b++) prm.shift[b] = (uint8_t)c.blocks[b].shift;
     const size_t warp_bytes = ((4u * CWW * x2_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kX2Warps;
     auto kern = decode_ms_tc_i8x2_kernel<M, FRONT>;
@@ -252,7 +250,7 @@ cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     if (e != cudaSuccess) return e;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kX2Warps, smem, stream>>>(
-        prm, static_cast<const typename FrontSrc<FRONT, int8_t>::type *>(llrs), output, (unsigned long long)batch, mi,
+        static_cast<const typename FrontSrc<FRONT, int8_t>::type *>(llrs), output, (unsigned long long)batch, mi,
         success, iters, counter, front.scale, front.limit);
     count_launch();
     return cudaGetLastError();
@@ -261,6 +259,7 @@ cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
 template <int M>
 bool x2_dispatch(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch, size_t max_iters,
                  uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err, const Front &front) {
+    if (!tc_const_shifts_match<M>(c)) return false;
     switch (front.kind) {
         case kFrontNone: *err = launch_x2<M, kFrontNone>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front); return true;
         case kFrontSoftF32: *err = launch_x2<M, kFrontSoftF32>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front); return true;
