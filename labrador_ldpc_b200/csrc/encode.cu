@@ -1,4 +1,6 @@
-// Batched systematic encoder: bit-packed GF(2) XOR over the compact generator.
+// Batched systematic encoders that work from the compact generator: the bit-packed GF(2) XOR kernel
+// (encode_kernel) and the TC-code table kernel (encode_tc_lut_kernel).  The TM codes are encoded through the
+// sparse parity-check matrix instead (encode_tm.cu); launch_encode() below picks the kernel.
 //
 // Replaces EncodeInto::encode_parity for u8/u32/u64 and LDPCCode::encode /
 // copy_encode (reference src/encoder.rs:41-82, 107-160, 189-252, 292-315).
@@ -6,12 +8,14 @@
 // The reference XORs generator row `crow` into the parity for every set data
 // bit crow*b + o and rotates each b-bit parity block left once per offset, so
 // the row contributed by data bit (crow, o) is the compact row gc[crow] with
-// every b-bit block rotated RIGHT by o.  Here one thread owns one 32-bit
-// parity word (MSB = lowest bit index, the reference's byte order) and, for
-// every set data bit, XORs in the matching 32-bit window of the rotated row,
-// taken with one funnel shift from two adjacent words of the row's block.
-// The compact generator (<= 4 KB) and the frame's data words sit in shared
-// memory.  No tensor cores: this is GF(2), not a real-valued contraction.
+// every b-bit block rotated RIGHT by o.
+//   * encode_kernel: one thread owns one (or WPT) 32-bit parity word(s) (MSB = lowest bit index, the
+//     reference's byte order) and, for every set data bit, XORs in the matching 32-bit window of the rotated
+//     row, taken with one funnel shift from two adjacent words of the row's block.  The compact generator
+//     (<= 4 KB) and the frame's data words sit in shared memory.  Small TC batches; A/B reference for the rest.
+//   * encode_tc_lut_kernel: TC codes, one codeword per thread over a table of per-byte / per-nibble parity
+//     contributions (see the comment at the kernel).
+// No tensor cores: this is GF(2), not a real-valued contraction.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
