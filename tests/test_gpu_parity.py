@@ -205,6 +205,43 @@ def test_encode_large_batch_and_unaligned(ldpc, oracle, code):
     assert int(dst[:2].sum()) == 0 and int(dst[2 + small * nb:].sum()) == 0
 
 
+def test_concurrent_host_threads(ldpc, oracle):
+    """The reference is re-entrant and its perftest calls it from every core at once
+    (perftest/src/main.rs:39-45); the drop-in must give every thread its own correct answer."""
+    import threading
+    jobs = []
+    for t in range(8):
+        code = (0, 2, 5, 8, 3, 1, 6, 7)[t]
+        data, cw, llrs = make_frames(oracle, code, 6, EBN0[code] + 1.0, seed=700 + t, ty="i8")
+        jobs.append((code, data, cw, llrs, oracle.decode_ms_batch(code, llrs, 50, nthreads=2)))
+    errors = []
+
+    def worker(job):
+        code, data, cw, llrs, want = job
+        c = ldpc.LDPCCode(code)
+        try:
+            for rep in range(5):
+                for f in range(data.shape[0]):                   # single-codeword reference-signature calls
+                    out = np.zeros(c.n() // 8, np.uint8)
+                    c.copy_encode(data[f], out)
+                    assert np.array_equal(out, cw[f])
+                    dec = np.zeros(c.output_len(), np.uint8)
+                    ok, it = c.decode_ms(llrs[f], dec, maxiters=50)
+                    assert np.array_equal(dec, want[0][f]) and bool(ok) == bool(want[1][f]) and int(it) == int(want[2][f])
+                got = c.decode_ms_batch(llrs, 50)                # and a batched call from host memory
+                assert_exact(got, want, NAMES[code] + " threaded")
+                assert np.array_equal(c.copy_encode_batch(data), cw)
+        except Exception as e:                                   # noqa: BLE001
+            errors.append((code, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_generator_encoder_stays_exact():
     """The TM codes are encoded through the parity-check matrix (encode_tm.cu); the generator kernel
     (LABRADOR_LDPC_ENC_GENERATOR=1) is the A/B reference and must stay bit-exact as well."""
