@@ -17,11 +17,11 @@
 // w = element 32 w + i), each lane owning one word (M = 2048: two) of every block column; identity blocks
 // connect a lane's own words, pi_k blocks read a 32-bit window lo[i] : hi[i] from shared memory.  A^-1 is
 // a 4 x 4 array of Q x Q circulants.  Two forms of the dense product:
-//   * LUT (large batches): a nibble lookup table in shared memory ("four Russians", code_tables.h:
+//   * LUT (the default): a nibble lookup table in shared memory ("four Russians", code_tables.h:
 //     tm_encoder_lut, 8 ... 128 KB): every nibble of s selects one pre-combined, pre-shifted row of M bits that is
 //     XORed into the codeword's words of p_CC -- one LDS + one LOP3 per word, no branches, no bit scans;
-//   * compact (a handful of codewords, where filling the table would dominate): the 16 first columns (<= 1 KB);
-//     every set bit y of s XORs the window of the column rotated by y (one funnel shift).
+//   * compact (A/B reference, LABRADOR_LDPC_ENC_TM_FORM=1): the 16 first columns (<= 1 KB); every set bit y of s
+//     XORs the window of the column rotated by y (one funnel shift); bound by the XU pipe (BREV + FLO per bit).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -351,12 +351,12 @@ cudaError_t launch_enc_tm_form(DeviceCtx &ctx, const CodeInfo &c, const DeviceCo
 template <int RATE, int M>
 cudaError_t launch_enc_tm(DeviceCtx &ctx, const CodeInfo &c, const DeviceCode &dc, const uint8_t *data,
                           uint8_t *codewords, size_t batch, cudaStream_t stream) {
-    // The LUT form fills 8 ... 128 KB of shared memory per CTA before the first codeword; it pays once every warp
-    // of the grid has a few codeword groups to encode.  LABRADOR_LDPC_ENC_TM_FORM = 1 (compact) / 2 (LUT) forces one.
+    // The LUT form fills 8 ... 128 KB of shared memory per CTA before the first codeword, which costs less than the
+    // bit-serial dense step of the compact form even for ONE codeword (tools/enc_crossover.py: TM8192 21 vs 38 us per
+    // call at 64 codewords); the compact form stays as the A/B reference.
+    // LABRADOR_LDPC_ENC_TM_FORM = 1 (compact) / 2 (LUT) forces one.
     static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TM_FORM"); return e ? atoi(e) : 0; }();
-    constexpr int MW = M / 32, CWW = MW < 32 ? 32 / MW : 1;
-    const size_t groups = (batch + CWW - 1) / CWW;
-    const bool lut = forced ? forced == 2 : groups >= (size_t)ctx.sm_count * enc_lut_warps<M>() * 2;
+    const bool lut = forced != 1;
     if (lut && dc.enc_lut) return launch_enc_tm_form<RATE, M, true>(ctx, c, dc, data, codewords, batch, stream);
     return launch_enc_tm_form<RATE, M, false>(ctx, c, dc, data, codewords, batch, stream);
 }

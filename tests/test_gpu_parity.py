@@ -242,9 +242,11 @@ def test_concurrent_host_threads(ldpc, oracle):
     assert not errors, errors
 
 
-def test_generator_encoder_stays_exact():
-    """The TM codes are encoded through the parity-check matrix (encode_tm.cu); the generator kernel
-    (LABRADOR_LDPC_ENC_GENERATOR=1) is the A/B reference and must stay bit-exact as well."""
+@pytest.mark.parametrize("knob", ["LABRADOR_LDPC_ENC_GENERATOR=1", "LABRADOR_LDPC_ENC_TM_FORM=1", "LABRADOR_LDPC_ENC_TC_TABLE=1"])
+def test_alternative_encoder_kernels_stay_exact(knob):
+    """The default encoders are the table kernels (TM: through the parity-check matrix with a nibble table,
+    encode_tm.cu; TC: per-byte table on large batches).  The generator kernel, the compact TM form and the TC
+    table kernel on small batches are reachable through environment knobs and must stay bit-exact as well."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -253,13 +255,19 @@ import sys, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle")
 import labrador_ldpc_b200 as L, pyoracle
 o = pyoracle.Oracle()
-for code in range(3, 9):
+for code in range(9):
     c = L.LDPCCode(code)
-    d = np.random.default_rng(code).integers(0, 256, (300, c.k() // 8), dtype=np.uint8)
-    assert np.array_equal(c.copy_encode_batch(d), o.copy_encode_batch(code, d, nthreads=4)), code
+    d = np.random.default_rng(code).integers(0, 256, (301, c.k() // 8), dtype=np.uint8)
+    want = o.copy_encode_batch(code, d, nthreads=4)
+    assert np.array_equal(c.copy_encode_batch(d), want), code
+    assert np.array_equal(c.copy_encode_batch(d[:1]), want[:1]), code
+    ip = np.zeros_like(want); ip[:, : c.k() // 8] = d
+    c.encode_batch(ip)
+    assert np.array_equal(ip, want), code
 print("OK")
 ''' % (root, root)
-    env = dict(os.environ, LABRADOR_LDPC_ENC_GENERATOR="1")
+    name, value = knob.split("=")
+    env = dict(os.environ, **{name: value})
     out = subprocess.check_output([sys.executable, "-c", script], env=env, text=True)
     assert "OK" in out
 
