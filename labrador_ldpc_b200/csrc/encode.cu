@@ -307,10 +307,11 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
         cudaError_t err = cudaSuccess;
         if (launch_encode_tm(ctx, code, data, codewords, batch, stream, &err)) return err;
     }
-    // TC codes, large batches: one codeword per thread over a byte / nibble lookup table (filling the table costs
-    // 16-64 KB of L2 reads per CTA, so small batches stay on the generator kernel)
+    // TC codes: one codeword per thread over a byte / nibble lookup table.  Filling the table (2 / 64 / 32 KB per CTA)
+    // is hidden by the launch for TC128 / TC256 at every batch size; for TC512 it pays from about 32 Ki codewords
+    // (tools/enc_crossover.py), below that the generator kernel is as fast.  LABRADOR_LDPC_ENC_TC_TABLE=1: always.
     static const bool tc_table_always = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TC_TABLE"); return e && atoi(e) != 0; }();
-    if (!force_gen && code < 3 && dc.enc_tc_lut && (tc_table_always || batch >= (size_t)ctx.sm_count * 1024)) {
+    if (!force_gen && code < 3 && dc.enc_tc_lut && (tc_table_always || code < 2 || batch >= 32768)) {
         // group sizes: code_tables.h: tc_encoder_group_bits
         switch (code) {
             case 0: return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);
