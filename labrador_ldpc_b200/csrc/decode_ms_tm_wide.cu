@@ -29,8 +29,8 @@ namespace {
 constexpr int kMaxDegW = 18;
 
 template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
-__global__ void __launch_bounds__(NT)
-decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
+__device__ __forceinline__ void
+decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
                          uint8_t *__restrict__ out_all,
                          unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                          uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
@@ -314,6 +314,29 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
     }
 }
 
+// Two entry points over the same body.  __launch_bounds__(NT) lets ptxas trade registers for occupancy, which is right
+// for the 32-bit types (TM2048 f32: 64 registers, two CTAs per SM, 10.3 M cw/s; with the full register budget 8.4 M).
+// For f64 it picked 32-64 registers and spilled 1.5-2 KB per thread on the k = 4096 codes; __maxnreg__ hands it the
+// whole budget of one CTA per SM instead (TM5120 f64 0.46 -> 2.3 M cw/s, TM6144 0.53 -> 1.5 M).
+template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
+__global__ void __launch_bounds__(NT)
+decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
+                         uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
+                         uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
+                         unsigned long long *__restrict__ counter, const float fscale, const float flimit) {
+    decode_ms_tm_wide_body<RATE, M, T, NT, FRONT>(prm, llrs_all, out_all, batch, max_iters, success, iters_out, counter,
+                                                  fscale, flimit);
+}
+template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
+__global__ void __maxnreg__(65536 / NT > 255 ? 255 : 65536 / NT)
+decode_ms_tm_wide_kernel_allregs(const TmParams prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
+                                 uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
+                                 uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
+                                 unsigned long long *__restrict__ counter, const float fscale, const float flimit) {
+    decode_ms_tm_wide_body<RATE, M, T, NT, FRONT>(prm, llrs_all, out_all, batch, max_iters, success, iters_out, counter,
+                                                  fscale, flimit);
+}
+
 template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
 cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                         size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
@@ -322,7 +345,10 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
     constexpr int NP = count_p<P>(P::NB);
     const TmParams prm = make_params<RATE>(c);
     const size_t smem = sizeof(typename MsgStore<T>::type) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32;
-    auto kern = decode_ms_tm_wide_kernel<RATE, M, T, NT, FRONT>;
+    auto kern = [] {
+        if constexpr (std::is_same<T, double>::value) return &decode_ms_tm_wide_kernel_allregs<RATE, M, T, NT, FRONT>;
+        else return &decode_ms_tm_wide_kernel<RATE, M, T, NT, FRONT>;
+    }();
     static bool configured[16] = {};
     if (!configured[ctx.device & 15]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -417,6 +443,10 @@ bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void
             return dispatch_type<1, 1024, 512, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
+            if (llr_type == kF64 && front.kind == kFrontNone) {      // 512 threads x 128 registers instead of 1024 x 64
+                *err = launch_wide<0, 2048, double, 512>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
+                return true;
+            }
             return dispatch_type<0, 2048, 1024, false>(ctx, c, llr_type, llrs, output, batch, max_iters, success, iters, stream, err, front);
         default:
             return false;
