@@ -49,6 +49,9 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
     //   marginal VA = va + B in [0, 2B-1], saturating_add = one VIADDMNMX.RELU;  message C = MAXV - clamp(va - u, +-MAXV);
     //   check side: sign = bit BITS-1 of C, |v| = |C - MAXV|, kill = that bit of (C ^ old) & (C ^ (old + 1)).
     constexpr bool kBiased = std::is_same<T, int8_t>::value || std::is_same<T, int16_t>::value;
+    // only where the registers run out: 2 registers per f64 value of per-edge / per-column state against the budget
+    constexpr bool kPackOld = std::is_same<T, double>::value &&
+                              2 * (NB + (NB - count_p<P>(NB)) + NCOL) * (M / NT) + 40 > (65536 / NT > 255 ? 255 : 65536 / NT);
     constexpr int BITS = 8 * (int)sizeof(T);
     constexpr int kB = kBiased ? (1 << (BITS - 1)) : 0, kMaxV = kB - 1;
     static_assert(M % NT == 0 && NT % 32 == 0 && Q % 32 == 0, "whole warps per quarter");
@@ -87,7 +90,10 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
             llrs_all + frame * (unsigned long long)(FRONT == kFrontHard ? N / 8 : N);   // front.cuh
 
         // zero-initialised state, every call (:368, :374)
-        CT Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[NB][EPT];
+        CT Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[kPackOld ? 1 : NB][EPT];
+        // f64 on the k = 4096 codes: the self-correction rule (:422-426) needs only "old v negative" and "old v non-zero"
+        // of every edge; two bits instead of a 64-bit register per edge keep them (almost) out of local memory
+        uint32_t oldneg[(NB + 31) / 32][EPT], oldnz[(NB + 31) / 32][EPT];
 #pragma unroll
         for (int ei = 0; ei < EPT; ei++) {
             const int e = tid + ei * NT;
@@ -99,7 +105,9 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][ei] = A::zero();
 #pragma unroll
-            for (int b = 0; b < NB; b++) vold[b][ei] = kBiased ? (CT)kMaxV : A::zero();
+            for (int b = 0; b < (kPackOld ? 1 : NB); b++) vold[b][ei] = kBiased ? (CT)kMaxV : A::zero();
+#pragma unroll
+            for (int w = 0; w < (NB + 31) / 32; w++) { oldneg[w][ei] = 0; oldnz[w][ei] = 0; }
 #pragma unroll
             for (int p = 0; p < NP; p++) msg[p * M + e] = (ST)A::zero();
         }
@@ -219,10 +227,20 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
                             CT nv;
                             if constexpr (P::blk(b).isp) nv = (CT)msg[count_p<P>(b) * M + e];
                             else nv = idm[count_i<P>(b)][ei];
-                            const CT vo = vold[b][ei];
-                            const bool keep = (A::hard_bit(nv) == A::hard_bit(vo)) || (vo == A::zero());
-                            const CT v = keep ? nv : A::zero();                       // :422-426
-                            vold[b][ei] = v;
+                            CT v;
+                            if constexpr (kPackOld) {
+                                constexpr int w = b / 32;
+                                constexpr uint32_t bit = 1u << (b % 32);
+                                const bool keep = (A::hard_bit(nv) == ((oldneg[w][ei] & bit) != 0)) || (oldnz[w][ei] & bit) == 0;
+                                v = keep ? nv : A::zero();                            // :422-426
+                                oldneg[w][ei] = A::hard_bit(v) ? (oldneg[w][ei] | bit) : (oldneg[w][ei] & ~bit);
+                                oldnz[w][ei] = (v == A::zero()) ? (oldnz[w][ei] & ~bit) : (oldnz[w][ei] | bit);
+                            } else {
+                                const CT vo = vold[b][ei];
+                                const bool keep = (A::hard_bit(nv) == A::hard_bit(vo)) || (vo == A::zero());
+                                v = keep ? nv : A::zero();                            // :422-426
+                                vold[b][ei] = v;
+                            }
                             a[k] = A::abs(v);
                             sg[k] = A::hard_bit(v);
                             stot ^= sg[k];                                            // :439-441
