@@ -214,6 +214,7 @@ void runtime_shutdown() {
             if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
         }
         if (c->vscratch) cudaFree(c->vscratch);
+        if (c->small_host) cudaFreeHost(c->small_host);
         if (c->retry_done) { cudaEventSynchronize(c->retry_done); cudaEventDestroy(c->retry_done); }
         if (c->retry_list) cudaFree(c->retry_list);
         if (c->table_blob) cudaFree(c->table_blob);
@@ -329,6 +330,38 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
     size_t per_frame = 0;
     for (const HostArray &a : arrays) per_frame += align_up(a.bytes_per_frame, 16);
     if (per_frame == 0 || count == 0) return LDPC_OK;
+    // Small calls (the reference's single-codeword API is a batch of one): the arrays are packed into one pinned,
+    // device-mapped block; the kernel reads its input and writes its results through that mapping, so the call is two
+    // host memcpys, one launch and one stream synchronisation instead of a staged copy per array (profiles/r01_latency.md).
+    static const bool small_path = [] { const char *e = getenv("LABRADOR_LDPC_SMALL_CALLS"); return !e || atoi(e) != 0; }();
+    if (small_path && per_frame * count + 256 * arrays.size() <= DeviceCtx::kSmallBytes) {
+        if (!ctx.small_host) {
+            CUDA_TRY(cudaHostAlloc(&ctx.small_host, DeviceCtx::kSmallBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+            CUDA_TRY(cudaHostGetDevicePointer(&ctx.small_dev, ctx.small_host, 0));
+        }
+        std::vector<void *> dptr(arrays.size());
+        std::vector<size_t> off(arrays.size());
+        size_t total = 0;
+        for (size_t i = 0; i < arrays.size(); i++) {
+            off[i] = total;
+            total += align_up(arrays[i].bytes_per_frame * count, 256);
+            dptr[i] = static_cast<unsigned char *>(ctx.small_dev) + off[i];
+            if (arrays[i].host_in)
+                memcpy(static_cast<unsigned char *>(ctx.small_host) + off[i],
+                       static_cast<const unsigned char *>(arrays[i].host_in) + first * arrays[i].bytes_per_frame,
+                       arrays[i].bytes_per_frame * count);
+        }
+        cudaStream_t st = ctx.pipe_stream[0];
+        cudaError_t e = launch(ctx, dptr, count, st, first);
+        if (e != cudaSuccess) return cuda_error(e, "kernel launch");
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return cuda_error(e, "stream synchronize");
+        for (size_t i = 0; i < arrays.size(); i++)
+            if (arrays[i].host_out)
+                memcpy(static_cast<unsigned char *>(arrays[i].host_out) + first * arrays[i].bytes_per_frame,
+                       static_cast<unsigned char *>(ctx.small_host) + off[i], arrays[i].bytes_per_frame * count);
+        return LDPC_OK;
+    }
     size_t chunk = chunk_bytes_target() / per_frame;
     const size_t min_chunk = (size_t)ctx.sm_count * 8;
     if (chunk < min_chunk) chunk = min_chunk;

@@ -67,6 +67,10 @@ struct DeviceCtx {
     unsigned *retry_list = nullptr;
     size_t retry_list_bytes = 0;
     cudaEvent_t retry_done = nullptr;
+    // small host-pointer calls (the single-codeword reference API): one pinned, device-mapped staging block
+    void *small_host = nullptr;   // host address
+    void *small_dev = nullptr;    // the same block as the device sees it
+    static constexpr size_t kSmallBytes = 256 << 10;
     // host-pointer pipeline
     static constexpr int kPipe = 3;
     cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
