@@ -205,6 +205,26 @@ def test_encode_large_batch_and_unaligned(ldpc, oracle, code):
     assert int(dst[:2].sum()) == 0 and int(dst[2 + small * nb:].sum()) == 0
 
 
+def test_small_call_staging_boundary(ldpc, oracle):
+    """Host-pointer calls of up to 256 KB go through the pinned, device-mapped staging block, larger ones through
+    the chunk pipeline (csrc/runtime.cu); batches on both sides of the boundary must agree with the oracle."""
+    code = 5
+    c = ldpc.LDPCCode(code)
+    _, _, llrs = make_frames(oracle, code, 130, 2.4, seed=321, ty="i8")
+    want = oracle.decode_ms_batch(code, llrs, 60, nthreads=8)
+    for batch in (1, 2, 105, 108, 109, 110, 111, 112, 130):     # 256 KB / (2048 + 320 + 1 + 4 bytes, 16-byte rounded) = 110.x frames
+        got = c.decode_ms_batch(llrs[:batch], 60)
+        assert_exact(got, tuple(w[:batch] for w in want), "batch %d" % batch)
+    data = np.random.default_rng(5).integers(0, 256, (700, c.k() // 8), dtype=np.uint8)
+    cw = oracle.copy_encode_batch(code, data, nthreads=4)
+    for batch in (1, 680, 682, 683, 684, 700):                   # 256 KB / (128 + 256) = 682.6 frames
+        assert np.array_equal(c.copy_encode_batch(data[:batch]), cw[:batch]), batch
+        ip = np.zeros((batch, c.n() // 8), np.uint8)
+        ip[:, : c.k() // 8] = data[:batch]
+        c.encode_batch(ip)
+        assert np.array_equal(ip, cw[:batch]), batch
+
+
 def test_concurrent_host_threads(ldpc, oracle):
     """The reference is re-entrant and its perftest calls it from every core at once
     (perftest/src/main.rs:39-45); the drop-in must give every thread its own correct answer."""
