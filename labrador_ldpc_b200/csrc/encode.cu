@@ -270,6 +270,112 @@ cudaError_t launch_encode_tc_lut(DeviceCtx &ctx, const DeviceCode &dc, const uin
     return cudaGetLastError();
 }
 
+// TC512 (b = 64): byte rows of block position 0 only; a data byte at byte position y of its block row contributes the
+// row of position 0 with every 8-byte parity block rotated by y bytes (two PRMT per block) -- 32 lookups of 32 bytes
+// instead of 64 with nibble rows (code_tables.h: tc512_encoder_lut).
+__host__ __device__ constexpr uint32_t rot_sel(int y, int half) {      // PRMT selector: result byte q <- block byte (q + 4 half - y) mod 8
+    uint32_t s = 0;
+    for (int q = 0; q < 4; q++) s |= (uint32_t)((q + 4 * half - y) & 7) << (4 * q);
+    return s;
+}
+
+__global__ void __launch_bounds__(512, 2)
+encode_tc512_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restrict__ data_all, uint8_t *__restrict__ cw_all,
+                    unsigned long long batch, const uint32_t row_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int KW = 8, LUTW = 4 * 256 * KW;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(lut_g);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < LUTW / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(cw_all) | reinterpret_cast<uintptr_t>(data_all)) & 15u) == 0;
+    const unsigned long long in_stride = data_all ? KW * 4ull : KW * 8ull;
+    const uint8_t *in_base = data_all ? data_all : cw_all;
+
+    for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < batch;
+         f += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint8_t *in = in_base + f * in_stride;
+        uint8_t *cw = cw_all + f * (KW * 8ull);
+        uint32_t d[KW], p[KW];
+        if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const uint4 v = reinterpret_cast<const uint4 *>(in)[i];
+                d[4 * i] = v.x; d[4 * i + 1] = v.y; d[4 * i + 2] = v.z; d[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < KW; w++)
+                d[w] = (uint32_t)in[4 * w] | ((uint32_t)in[4 * w + 1] << 8) | ((uint32_t)in[4 * w + 2] << 16) | ((uint32_t)in[4 * w + 3] << 24);
+        }
+#pragma unroll
+        for (int w = 0; w < KW; w++) p[w] = 0;
+#pragma unroll
+        for (int w = 0; w < KW; w++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int j = 4 * w + b, crow = j / 8, y = j % 8;           // compile-time after unrolling
+                const uint32_t byte = __byte_perm(d[w], 0, 0x4440 + b);
+                const uint32_t a = lut_sa + (uint32_t)(crow * 256 * KW * 4) + byte * row_bytes;
+                uint32_t t[8];
+                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]) : "r"(a));
+                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]) : "r"(a + 16));
+#pragma unroll
+                for (int blk = 0; blk < 4; blk++) {
+                    if (y == 0) {
+                        p[2 * blk] ^= t[2 * blk];
+                        p[2 * blk + 1] ^= t[2 * blk + 1];
+                    } else {
+                        p[2 * blk] ^= __byte_perm(t[2 * blk], t[2 * blk + 1], rot_sel(y, 0));
+                        p[2 * blk + 1] ^= __byte_perm(t[2 * blk], t[2 * blk + 1], rot_sel(y, 1));
+                    }
+                }
+            }
+        }
+        if (vec_ok) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (data_all) reinterpret_cast<uint4 *>(cw)[i] = make_uint4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
+                reinterpret_cast<uint4 *>(cw)[2 + i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < KW; w++) {
+                if (data_all) {
+                    cw[4 * w] = (uint8_t)d[w]; cw[4 * w + 1] = (uint8_t)(d[w] >> 8);
+                    cw[4 * w + 2] = (uint8_t)(d[w] >> 16); cw[4 * w + 3] = (uint8_t)(d[w] >> 24);
+                }
+                uint8_t *o = cw + KW * 4 + 4 * w;
+                o[0] = (uint8_t)p[w]; o[1] = (uint8_t)(p[w] >> 8); o[2] = (uint8_t)(p[w] >> 16); o[3] = (uint8_t)(p[w] >> 24);
+            }
+        }
+    }
+}
+
+cudaError_t launch_encode_tc512(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords, size_t batch,
+                                cudaStream_t stream) {
+    constexpr int threads = 512;
+    const size_t smem = 4 * 256 * 8 * 4;
+    static bool configured[16] = {};
+    static int per_sm_cached[16] = {};
+    if (!configured[ctx.device & 15]) {
+        int per_sm = 1;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tc512_kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device & 15] = true;
+    }
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    const unsigned long long need = (batch + threads - 1) / threads;
+    if (grid > need) grid = need;
+    encode_tc512_kernel<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, 32u);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int WPT>
 cudaError_t launch_encode_wpt(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords,
                               size_t batch, cudaStream_t stream) {
@@ -316,7 +422,7 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
         switch (code) {
             case 0: return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);
             case 1: return launch_encode_tc_lut<4, 8>(ctx, dc, data, codewords, batch, stream);
-            default: return launch_encode_tc_lut<8, 4>(ctx, dc, data, codewords, batch, stream);
+            default: return launch_encode_tc512(ctx, dc, data, codewords, batch, stream);
         }
     }
     // words per thread: the number of circulant blocks per row (n-k)/b must be divisible by it
