@@ -345,6 +345,25 @@ def test_decode_ms_float_awgn(ldpc, oracle, code, ty):
     assert_float_parity(got, want, "%s %s" % (NAMES[code], ty))
 
 
+@pytest.mark.parametrize("code", [2, 3, 5, 6, 7, 8])
+@pytest.mark.parametrize("ty", ["f32", "f64"])
+def test_decode_ms_float_small_integer_llrs_exact(ldpc, oracle, code, ty):
+    """Float LLRs that are small integers (with many exact zeros and some -0.0): every sum is exact, so the result
+    does not depend on the order of additions and must equal the oracle's bit for bit -- while ties, zero messages
+    (the `v_old == 0` arm of the self-correction rule, src/decoder.rs:422-426) and negative zeros are everywhere."""
+    c = ldpc.LDPCCode(code)
+    rng = np.random.default_rng(4000 + code)
+    batch = 40 if code < 6 else 24
+    _, cw, _ = make_frames(oracle, code, batch, 3.0, seed=50 + code, ty="i8")
+    bits = np.unpackbits(cw, axis=1)[:, : c.n()].astype(np.int64)
+    llrs = (1 - 2 * bits) * rng.integers(0, 4, bits.shape) + rng.integers(-1, 2, bits.shape)
+    llrs = llrs.astype(np.float32 if ty == "f32" else np.float64)
+    llrs[rng.random(llrs.shape) < 0.05] = -0.0
+    want = oracle.decode_ms_batch(code, llrs, 25, nthreads=8)
+    got = c.decode_ms_batch(llrs, 25)
+    assert_exact(got, want, "%s %s" % (NAMES[code], ty))
+
+
 @pytest.mark.parametrize("code", CODES)
 def test_decode_ms_i8_saturation_stress(ldpc, oracle, code):
     """Full-range random LLRs: decoding fails, every saturating add/sub/abs corner is hit
