@@ -254,17 +254,17 @@ bool tc_encoder_lut(int code, int group_bits, std::vector<uint32_t> &lut) {
     return true;
 }
 
-bool tc512_encoder_lut(std::vector<uint32_t> &lut) {
+bool tc_rot_encoder_lut(int code, std::vector<uint32_t> &lut) {
     lut.clear();
-    const CodeInfo *ci = code_info(2);
-    if (!ci || ci->b != 64 || ci->k != 256 || ci->n != 512) return false;
+    const CodeInfo *ci = code_info(code);
+    if (!ci || ci->p != 0 || ci->b % 32 != 0 || ci->k != 4 * ci->b) return false;
     std::vector<uint32_t> full;
-    if (!tc_encoder_lut(2, 8, full)) return false;
-    const int KW = 8;
+    if (!tc_encoder_lut(code, 8, full)) return false;
+    const int KW = (ci->n - ci->k) / 32, BB = ci->b / 8;
     lut.assign((size_t)4 * 256 * KW, 0);
     for (int crow = 0; crow < 4; crow++)
         for (int v = 0; v < 256; v++)
-            for (int w = 0; w < KW; w++) lut[((size_t)crow * 256 + v) * KW + w] = full[((size_t)(crow * 8) * 256 + v) * KW + w];
+            for (int w = 0; w < KW; w++) lut[((size_t)crow * 256 + v) * KW + w] = full[((size_t)(crow * BB) * 256 + v) * KW + w];
     return true;
 }
 
@@ -297,17 +297,18 @@ bool host_encode_tables(int code, const uint8_t *data, uint8_t *parity) {
     const CodeInfo *ci = code_info(code);
     if (!ci) return false;
     const CodeInfo &c = *ci;
-    if (code == 2) {                                         // TC512: byte rows of block position 0, rotated by whole bytes
+    if (code == 1 || code == 2) {                            // TC256 / TC512: byte rows of block position 0, rotated by whole bytes
         std::vector<uint32_t> lut;
-        if (!tc512_encoder_lut(lut)) return false;
-        uint8_t out[32] = {0};
-        for (int j = 0; j < 32; j++) {
-            const int crow = j / 8, y = j % 8;
-            const uint8_t *row = reinterpret_cast<const uint8_t *>(&lut[((size_t)crow * 256 + data[j]) * 8]);   // little-endian words = memory order
-            for (int blk = 0; blk < 4; blk++)
-                for (int q = 0; q < 8; q++) out[blk * 8 + q] ^= row[blk * 8 + ((q - y) & 7)];
+        if (!tc_rot_encoder_lut(code, lut)) return false;
+        const int PB = (c.n - c.k) / 8, BB = c.b / 8;        // parity bytes, bytes per circulant block
+        std::vector<uint8_t> out(PB, 0);
+        for (int j = 0; j < c.k / 8; j++) {
+            const int crow = j / BB, y = j % BB;
+            const uint8_t *row = reinterpret_cast<const uint8_t *>(&lut[((size_t)crow * 256 + data[j]) * (PB / 4)]);   // little-endian words = memory order
+            for (int blk = 0; blk < PB / BB; blk++)
+                for (int q = 0; q < BB; q++) out[blk * BB + q] ^= row[blk * BB + ((q - y) & (BB - 1))];
         }
-        for (int i = 0; i < 32; i++) parity[i] = out[i];
+        for (int i = 0; i < PB; i++) parity[i] = out[i];
         return true;
     }
     if (c.p == 0) {                                          // TC codes: encode_tc_lut_kernel

@@ -98,11 +98,11 @@ bool tc_encoder_lut(int code, int group_bits, std::vector<uint32_t> &lut);
 // group size the table kernel is instantiated with: nibble rows for TC128 (16 rows = one sweep of the 32 banks, so a
 // load never conflicts) and TC512 (table size), byte rows for TC256
 inline int tc_encoder_group_bits(int code) { return code == 1 ? 8 : 4; }
-// TC512 (b = 64: a circulant block is 8 whole bytes): a data byte at byte position y of its block row contributes
-// what the byte at position 0 contributes with every 8-byte parity block rotated by y bytes, so only the rows of
-// position 0 are tabulated -- 4 block rows x 256 values x 32 bytes = 32 KB, half as many lookups as nibble rows:
-//     lut[(crow * 256 + v) * 8 + w]
-bool tc512_encoder_lut(std::vector<uint32_t> &lut);
+// TC256 / TC512 (b = 32 / 64: a circulant block is 4 / 8 whole bytes): a data byte at byte position y of its block row
+// contributes what the byte at position 0 contributes with every parity block rotated by y bytes, so only the rows of
+// position 0 are tabulated -- 4 block rows x 256 values x (n-k)/8 bytes = 16 / 32 KB:
+//     lut[(crow * 256 + v) * (n-k)/32 + w]
+bool tc_rot_encoder_lut(int code, std::vector<uint32_t> &lut);
 
 // Host-side models of the encoders, for the CPU tests (tests/test_capi_host.py): the parity bytes of one data block
 //   * host_encode_generator: by the compact generator, the reference's algorithm (src/encoder.rs:42-82);

@@ -13,8 +13,8 @@
 //     reference's byte order) and, for every set data bit, XORs in the matching 32-bit window of the rotated
 //     row, taken with one funnel shift from two adjacent words of the row's block.  The compact generator
 //     (<= 4 KB) and the frame's data words sit in shared memory.  Small TC batches; A/B reference for the rest.
-//   * encode_tc_lut_kernel: TC codes, one codeword per thread over a table of per-byte / per-nibble parity
-//     contributions (see the comment at the kernel).
+//   * encode_tc_lut_kernel (TC128) / encode_tc_rot_kernel (TC256, TC512): one codeword per thread over a table of
+//     per-nibble / per-byte parity contributions (see the comments at the kernels).
 // No tensor cores: this is GF(2), not a real-valued contraction.
 #include <cuda_runtime.h>
 
@@ -270,20 +270,23 @@ cudaError_t launch_encode_tc_lut(DeviceCtx &ctx, const DeviceCode &dc, const uin
     return cudaGetLastError();
 }
 
-// TC512 (b = 64): byte rows of block position 0 only; a data byte at byte position y of its block row contributes the
-// row of position 0 with every 8-byte parity block rotated by y bytes (two PRMT per block) -- 32 lookups of 32 bytes
-// instead of 64 with nibble rows (code_tables.h: tc512_encoder_lut).
-__host__ __device__ constexpr uint32_t rot_sel(int y, int half) {      // PRMT selector: result byte q <- block byte (q + 4 half - y) mod 8
+// TC256 / TC512 (b = 32 / 64: a circulant block is BW = 1 / 2 whole words): byte rows of block position 0 only; a data
+// byte at byte position y of its block row contributes the row of position 0 with every parity block rotated by y
+// bytes (one PRMT per word) -- k/8 lookups over a 16 / 32 KB table (code_tables.h: tc_rot_encoder_lut) instead of a
+// 64 KB byte table / k/4 lookups with nibble rows.
+template <int BW> __host__ __device__ constexpr uint32_t rot_sel(int y, int half) {
+    // PRMT selector: result byte q of word `half` of a block <- block byte (q + 4 half - y) mod (4 BW)
     uint32_t s = 0;
-    for (int q = 0; q < 4; q++) s |= (uint32_t)((q + 4 * half - y) & 7) << (4 * q);
+    for (int q = 0; q < 4; q++) s |= (uint32_t)((q + 4 * half - y) & (4 * BW - 1)) << (4 * q);
     return s;
 }
 
+template <int KW>
 __global__ void __launch_bounds__(512, 2)
-encode_tc512_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restrict__ data_all, uint8_t *__restrict__ cw_all,
-                    unsigned long long batch, const uint32_t row_bytes) {
+encode_tc_rot_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restrict__ data_all, uint8_t *__restrict__ cw_all,
+                     unsigned long long batch, const uint32_t row_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int KW = 8, LUTW = 4 * 256 * KW;
+    constexpr int LUTW = 4 * 256 * KW, BW = KW / 4, BB = 4 * BW, NVEC = KW / 4;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(lut_g);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
@@ -302,7 +305,7 @@ encode_tc512_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restric
         uint32_t d[KW], p[KW];
         if (vec_ok) {
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < NVEC; i++) {
                 const uint4 v = reinterpret_cast<const uint4 *>(in)[i];
                 d[4 * i] = v.x; d[4 * i + 1] = v.y; d[4 * i + 2] = v.z; d[4 * i + 3] = v.w;
             }
@@ -317,29 +320,33 @@ encode_tc512_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restric
         for (int w = 0; w < KW; w++) {
 #pragma unroll
             for (int b = 0; b < 4; b++) {
-                const int j = 4 * w + b, crow = j / 8, y = j % 8;           // compile-time after unrolling
+                const int j = 4 * w + b, crow = j / BB, y = j % BB;         // compile-time after unrolling
                 const uint32_t byte = __byte_perm(d[w], 0, 0x4440 + b);
                 const uint32_t a = lut_sa + (uint32_t)(crow * 256 * KW * 4) + byte * row_bytes;
-                uint32_t t[8];
-                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]) : "r"(a));
-                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]) : "r"(a + 16));
+                uint32_t t[KW];
+#pragma unroll
+                for (int i = 0; i < NVEC; i++)
+                    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                        : "=r"(t[4 * i]), "=r"(t[4 * i + 1]), "=r"(t[4 * i + 2]), "=r"(t[4 * i + 3]) : "r"(a + 16 * i));
 #pragma unroll
                 for (int blk = 0; blk < 4; blk++) {
                     if (y == 0) {
-                        p[2 * blk] ^= t[2 * blk];
-                        p[2 * blk + 1] ^= t[2 * blk + 1];
+#pragma unroll
+                        for (int h = 0; h < BW; h++) p[BW * blk + h] ^= t[BW * blk + h];
+                    } else if constexpr (BW == 1) {
+                        p[blk] ^= __byte_perm(t[blk], t[blk], rot_sel<1>(y, 0));
                     } else {
-                        p[2 * blk] ^= __byte_perm(t[2 * blk], t[2 * blk + 1], rot_sel(y, 0));
-                        p[2 * blk + 1] ^= __byte_perm(t[2 * blk], t[2 * blk + 1], rot_sel(y, 1));
+                        p[2 * blk] ^= __byte_perm(t[2 * blk], t[2 * blk + 1], rot_sel<2>(y, 0));
+                        p[2 * blk + 1] ^= __byte_perm(t[2 * blk], t[2 * blk + 1], rot_sel<2>(y, 1));
                     }
                 }
             }
         }
         if (vec_ok) {
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
+            for (int i = 0; i < NVEC; i++) {
                 if (data_all) reinterpret_cast<uint4 *>(cw)[i] = make_uint4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]);
-                reinterpret_cast<uint4 *>(cw)[2 + i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+                reinterpret_cast<uint4 *>(cw)[NVEC + i] = make_uint4(p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
             }
         } else {
 #pragma unroll
@@ -355,15 +362,16 @@ encode_tc512_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restric
     }
 }
 
-cudaError_t launch_encode_tc512(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords, size_t batch,
-                                cudaStream_t stream) {
+template <int KW>
+cudaError_t launch_encode_tc_rot(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords, size_t batch,
+                                 cudaStream_t stream) {
     constexpr int threads = 512;
-    const size_t smem = 4 * 256 * 8 * 4;
+    const size_t smem = 4 * 256 * KW * 4;
     static bool configured[16] = {};
     static int per_sm_cached[16] = {};
     if (!configured[ctx.device & 15]) {
         int per_sm = 1;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tc512_kernel, threads, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tc_rot_kernel<KW>, threads, smem);
         if (e != cudaSuccess) return e;
         per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
         configured[ctx.device & 15] = true;
@@ -371,7 +379,7 @@ cudaError_t launch_encode_tc512(DeviceCtx &ctx, const DeviceCode &dc, const uint
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
     const unsigned long long need = (batch + threads - 1) / threads;
     if (grid > need) grid = need;
-    encode_tc512_kernel<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, 32u);
+    encode_tc_rot_kernel<KW><<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, KW * 4u);
     count_launch();
     return cudaGetLastError();
 }
@@ -413,7 +421,7 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
         cudaError_t err = cudaSuccess;
         if (launch_encode_tm(ctx, code, data, codewords, batch, stream, &err)) return err;
     }
-    // TC codes: one codeword per thread over a byte / nibble lookup table.  Filling the table (2 / 64 / 32 KB per CTA)
+    // TC codes: one codeword per thread over a nibble / byte lookup table.  Filling the table (2 / 16 / 32 KB per CTA)
     // is hidden by the launch for TC128 / TC256 at every batch size; for TC512 it pays from about 32 Ki codewords
     // (tools/enc_crossover.py), below that the generator kernel is as fast.  LABRADOR_LDPC_ENC_TC_TABLE=1: always.
     static const bool tc_table_always = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TC_TABLE"); return e && atoi(e) != 0; }();
@@ -421,8 +429,8 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
         // group sizes: code_tables.h: tc_encoder_group_bits
         switch (code) {
             case 0: return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);
-            case 1: return launch_encode_tc_lut<4, 8>(ctx, dc, data, codewords, batch, stream);
-            default: return launch_encode_tc512(ctx, dc, data, codewords, batch, stream);
+            case 1: return launch_encode_tc_rot<4>(ctx, dc, data, codewords, batch, stream);
+            default: return launch_encode_tc_rot<8>(ctx, dc, data, codewords, batch, stream);
         }
     }
     // words per thread: the number of circulant blocks per row (n-k)/b must be divisible by it

@@ -114,7 +114,7 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         offs[ci].has_ainv = tm_encoder_table(ci, ainv);
         offs[ci].ainv = offs[ci].has_ainv ? append(ainv.data(), ainv.size() * 4) : 0;
         std::vector<uint32_t> tc_lut;
-        offs[ci].has_tc_lut = ci == 2 ? tc512_encoder_lut(tc_lut) : tc_encoder_lut(ci, tc_encoder_group_bits(ci), tc_lut);
+        offs[ci].has_tc_lut = (ci == 1 || ci == 2) ? tc_rot_encoder_lut(ci, tc_lut) : tc_encoder_lut(ci, tc_encoder_group_bits(ci), tc_lut);
         offs[ci].tc_lut = offs[ci].has_tc_lut ? append(tc_lut.data(), tc_lut.size() * 4) : 0;
         std::vector<uint32_t> lut;
         offs[ci].lut = (offs[ci].has_ainv && tm_encoder_lut(ci, lut)) ? append(lut.data(), lut.size() * 4) : 0;
