@@ -281,8 +281,11 @@ template <int BW> __host__ __device__ constexpr uint32_t rot_sel(int y, int half
     return s;
 }
 
-template <int KW>
-__global__ void __launch_bounds__(512, 2)
+// R = copies of the table in shared memory: lane l reads copy l mod R, whose rows sit R rows apart, so the lanes of a
+// quarter warp (one 128-byte wavefront of a 16-byte-per-lane load) fall into different banks whatever rows their data
+// select (R = 8 with 16-byte rows: never a conflict).  Costs R times the fill, so only large batches use R > 1.
+template <int KW, int R>
+__global__ void __launch_bounds__(R > 1 ? 1024 : 512, R > 1 ? 1 : 2)
 encode_tc_rot_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restrict__ data_all, uint8_t *__restrict__ cw_all,
                      unsigned long long batch, const uint32_t row_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -290,10 +293,15 @@ encode_tc_rot_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restri
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(lut_g);
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (int i = threadIdx.x; i < LUTW / 4; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < LUTW / 4; i += blockDim.x) {
+            const uint4 v = src[i];
+            const int row = i / NVEC, part = i % NVEC;
+#pragma unroll
+            for (int g = 0; g < R; g++) dst[(row * R + g) * NVEC + part] = v;
+        }
     }
     __syncthreads();
-    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(smem) + (threadIdx.x % R) * (KW * 4);
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(cw_all) | reinterpret_cast<uintptr_t>(data_all)) & 15u) == 0;
     const unsigned long long in_stride = data_all ? KW * 4ull : KW * 8ull;
     const uint8_t *in_base = data_all ? data_all : cw_all;
@@ -322,7 +330,7 @@ encode_tc_rot_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restri
             for (int b = 0; b < 4; b++) {
                 const int j = 4 * w + b, crow = j / BB, y = j % BB;         // compile-time after unrolling
                 const uint32_t byte = __byte_perm(d[w], 0, 0x4440 + b);
-                const uint32_t a = lut_sa + (uint32_t)(crow * 256 * KW * 4) + byte * row_bytes;
+                const uint32_t a = lut_sa + (uint32_t)(crow * 256 * KW * 4 * R) + byte * row_bytes;     // row_bytes = 4 KW R
                 uint32_t t[KW];
 #pragma unroll
                 for (int i = 0; i < NVEC; i++)
@@ -362,16 +370,19 @@ encode_tc_rot_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restri
     }
 }
 
-template <int KW>
-cudaError_t launch_encode_tc_rot(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords, size_t batch,
-                                 cudaStream_t stream) {
-    constexpr int threads = 512;
-    const size_t smem = 4 * 256 * KW * 4;
+template <int KW, int R>
+cudaError_t launch_encode_tc_rot_r(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords, size_t batch,
+                                   cudaStream_t stream) {
+    constexpr int threads = R > 1 ? 1024 : 512;
+    const size_t smem = (size_t)4 * 256 * KW * 4 * R;
+    auto kern = encode_tc_rot_kernel<KW, R>;
     static bool configured[16] = {};
     static int per_sm_cached[16] = {};
     if (!configured[ctx.device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         int per_sm = 1;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tc_rot_kernel<KW>, threads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
         if (e != cudaSuccess) return e;
         per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
         configured[ctx.device & 15] = true;
@@ -379,9 +390,21 @@ cudaError_t launch_encode_tc_rot(DeviceCtx &ctx, const DeviceCode &dc, const uin
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
     const unsigned long long need = (batch + threads - 1) / threads;
     if (grid > need) grid = need;
-    encode_tc_rot_kernel<KW><<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, KW * 4u);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, KW * 4u * R);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int KW>
+cudaError_t launch_encode_tc_rot(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords, size_t batch,
+                                 cudaStream_t stream) {
+    // Table copies (128 KB per CTA): TC256 (8 copies, no conflicts at all) costs nothing measurable even for one
+    // codeword; TC512 (4 copies) pays from about 128 Ki codewords (tools/enc_crossover.py).
+    // LABRADOR_LDPC_ENC_TC_COPIES=0 / 1: never / always.
+    static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TC_COPIES"); return e ? atoi(e) : -1; }();
+    const bool copies = forced >= 0 ? forced != 0 : (KW == 4 || batch >= (1u << 17));
+    if (copies) return launch_encode_tc_rot_r<KW, KW == 4 ? 8 : 4>(ctx, dc, data, codewords, batch, stream);
+    return launch_encode_tc_rot_r<KW, 1>(ctx, dc, data, codewords, batch, stream);
 }
 
 template <int WPT>
@@ -421,11 +444,9 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
         cudaError_t err = cudaSuccess;
         if (launch_encode_tm(ctx, code, data, codewords, batch, stream, &err)) return err;
     }
-    // TC codes: one codeword per thread over a nibble / byte lookup table.  Filling the table (2 / 16 / 32 KB per CTA)
-    // is hidden by the launch for TC128 / TC256 at every batch size; for TC512 it pays from about 32 Ki codewords
-    // (tools/enc_crossover.py), below that the generator kernel is as fast.  LABRADOR_LDPC_ENC_TC_TABLE=1: always.
-    static const bool tc_table_always = [] { const char *e = getenv("LABRADOR_LDPC_ENC_TC_TABLE"); return e && atoi(e) != 0; }();
-    if (!force_gen && code < 3 && dc.enc_tc_lut && (tc_table_always || code < 2 || batch >= 32768)) {
+    // TC codes: one codeword per thread over a nibble / byte lookup table, at every batch size (filling the table is
+    // hidden by the launch: tools/enc_crossover.py).  The generator kernel below remains as the A/B reference.
+    if (!force_gen && code < 3 && dc.enc_tc_lut) {
         // group sizes: code_tables.h: tc_encoder_group_bits
         switch (code) {
             case 0: return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);

@@ -262,11 +262,12 @@ def test_concurrent_host_threads(ldpc, oracle):
     assert not errors, errors
 
 
-@pytest.mark.parametrize("knob", ["LABRADOR_LDPC_ENC_GENERATOR=1", "LABRADOR_LDPC_ENC_TM_FORM=1", "LABRADOR_LDPC_ENC_TC_TABLE=1"])
+@pytest.mark.parametrize("knob", ["LABRADOR_LDPC_ENC_GENERATOR=1", "LABRADOR_LDPC_ENC_TM_FORM=1", "LABRADOR_LDPC_ENC_TC_COPIES=0", "LABRADOR_LDPC_ENC_TC_COPIES=1"])
 def test_alternative_encoder_kernels_stay_exact(knob):
     """The default encoders are the table kernels (TM: through the parity-check matrix with a nibble table,
-    encode_tm.cu; TC: per-byte table on large batches).  The generator kernel, the compact TM form and the TC
-    table kernel on small batches are reachable through environment knobs and must stay bit-exact as well."""
+    encode_tm.cu; TC: per-nibble / per-byte tables).  The generator kernel, the compact TM form and the TC table
+    kernels with / without bank-spreading table copies are reachable through environment knobs and must stay
+    bit-exact as well."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,5 +1,5 @@
 """Encoders: time of one copy_encode_batch call vs batch size (run once per LABRADOR_LDPC_ENC_TM_FORM=1 / 2,
-LABRADOR_LDPC_ENC_TC_TABLE=0 / 1, LABRADOR_LDPC_ENC_GENERATOR=1).   python tools/enc_crossover.py [codes...]"""
+LABRADOR_LDPC_ENC_TC_COPIES=0 / 1, LABRADOR_LDPC_ENC_GENERATOR=1).   python tools/enc_crossover.py [codes...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, labrador_ldpc_b200 as L

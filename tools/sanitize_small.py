@@ -37,7 +37,7 @@ for code in (0, 5):                                                             
     out = np.zeros((13, c.output_len()), np.uint8); out[:, : c.n() // 8] = cw
     assert not c.count_errors_batch(out, data).any()
 for code in range(9):                                                            # encoders, ragged batch, in place too
-    c = L.LDPCCode(code)                                                         # (LABRADOR_LDPC_ENC_TM_FORM=1: compact TM form; LABRADOR_LDPC_ENC_TC_TABLE=1: TC table kernel)
+    c = L.LDPCCode(code)                                                         # (LABRADOR_LDPC_ENC_TM_FORM=1: compact TM form; LABRADOR_LDPC_ENC_TC_COPIES=1: table copies for TC512 too; LABRADOR_LDPC_ENC_GENERATOR=1: generator kernel)
     d = np.random.default_rng(code).integers(0, 256, (37, c.k() // 8), dtype=np.uint8)
     want = o.copy_encode_batch(code, d, nthreads=4)
     assert np.array_equal(c.copy_encode_batch(d), want)
