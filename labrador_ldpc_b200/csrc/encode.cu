@@ -270,6 +270,88 @@ cudaError_t launch_encode_tc_lut(DeviceCtx &ctx, const DeviceCode &dc, const uin
     return cudaGetLastError();
 }
 
+
+// TC128, 16-byte-aligned buffers: two codewords per thread, so every global access is 16 bytes wide (one load of two
+// 8-byte data blocks, one store per 16-byte codeword) and twice as many bytes are in flight per thread.  Nibble rows as
+// in encode_tc_lut_kernel<2, 4> (the 16 rows of a position are one sweep of the banks: no conflicts).
+__global__ void __launch_bounds__(512, 2)
+encode_tc128_pair_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restrict__ data_all,
+                         uint8_t *__restrict__ cw_all, unsigned long long batch) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int LUTW = 16 * 16 * 2;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(lut_g);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (int i = threadIdx.x; i < LUTW / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(smem);
+    auto parity_of = [&](uint32_t d0, uint32_t d1, uint32_t &p0, uint32_t &p1) {
+        p0 = 0; p1 = 0;
+#pragma unroll
+        for (int w = 0; w < 2; w++) {
+            const uint32_t dw = w ? d1 : d0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t byte = __byte_perm(dw, 0, 0x4440 + b);
+                // high nibble = group 2j, low nibble = group 2j + 1 of byte j = 4w + b; 16 rows of 8 bytes per group
+                const uint32_t a_hi = lut_sa + (uint32_t)(((4 * w + b) * 2) * 128) + (byte >> 4) * 8u;
+                const uint32_t a_lo = lut_sa + (uint32_t)(((4 * w + b) * 2 + 1) * 128) + (byte & 15u) * 8u;
+                uint2 x, y;
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x.x), "=r"(x.y) : "r"(a_hi));
+                asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(y.x), "=r"(y.y) : "r"(a_lo));
+                p0 ^= x.x ^ y.x; p1 ^= x.y ^ y.y;
+            }
+        }
+    };
+    const unsigned long long pairs = batch / 2;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < pairs;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        uint4 *cw = reinterpret_cast<uint4 *>(cw_all) + 2 * t;
+        uint4 d;                                            // (A.d0, A.d1, B.d0, B.d1)
+        if (data_all) {
+            d = reinterpret_cast<const uint4 *>(data_all)[t];
+        } else {
+            const uint4 a = cw[0], b = cw[1];
+            d = make_uint4(a.x, a.y, b.x, b.y);
+        }
+        uint32_t pa0, pa1, pb0, pb1;
+        parity_of(d.x, d.y, pa0, pa1);
+        parity_of(d.z, d.w, pb0, pb1);
+        cw[0] = make_uint4(d.x, d.y, pa0, pa1);
+        cw[1] = make_uint4(d.z, d.w, pb0, pb1);
+    }
+    if ((batch & 1) && blockIdx.x == 0 && threadIdx.x == 0) {            // odd batch: the last codeword on its own
+        const unsigned long long f = batch - 1;
+        const uint2 dd = data_all ? reinterpret_cast<const uint2 *>(data_all)[f] : reinterpret_cast<const uint2 *>(cw_all)[2 * f];
+        uint32_t p0, p1;
+        parity_of(dd.x, dd.y, p0, p1);
+        reinterpret_cast<uint4 *>(cw_all)[f] = make_uint4(dd.x, dd.y, p0, p1);
+    }
+}
+
+cudaError_t launch_encode_tc128_pair(DeviceCtx &ctx, const DeviceCode &dc, const uint8_t *data, uint8_t *codewords,
+                                     size_t batch, cudaStream_t stream) {
+    constexpr int threads = 512;
+    const size_t smem = 16 * 16 * 2 * 4;
+    static bool configured[16] = {};
+    static int per_sm_cached[16] = {};
+    if (!configured[ctx.device & 15]) {
+        int per_sm = 1;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tc128_pair_kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device & 15] = true;
+    }
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    const unsigned long long need = (batch / 2 + threads - 1) / threads;
+    if (grid > need) grid = need;
+    if (grid == 0) grid = 1;
+    encode_tc128_pair_kernel<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // TC256 / TC512 (b = 32 / 64: a circulant block is BW = 1 / 2 whole words): byte rows of block position 0 only; a data
 // byte at byte position y of its block row contributes the row of position 0 with every parity block rotated by y
 // bytes (one PRMT per word) -- k/8 lookups over a 16 / 32 KB table (code_tables.h: tc_rot_encoder_lut) instead of a
@@ -449,7 +531,10 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
     if (!force_gen && code < 3 && dc.enc_tc_lut) {
         // group sizes: code_tables.h: tc_encoder_group_bits
         switch (code) {
-            case 0: return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);
+            case 0:
+                if (((reinterpret_cast<uintptr_t>(codewords) | reinterpret_cast<uintptr_t>(data)) & 15u) == 0)
+                    return launch_encode_tc128_pair(ctx, dc, data, codewords, batch, stream);
+                return launch_encode_tc_lut<2, 4>(ctx, dc, data, codewords, batch, stream);
             case 1: return launch_encode_tc_rot<4>(ctx, dc, data, codewords, batch, stream);
             default: return launch_encode_tc_rot<8>(ctx, dc, data, codewords, batch, stream);
         }
