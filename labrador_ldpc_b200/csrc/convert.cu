@@ -34,7 +34,7 @@ __global__ void hard_to_llrs_kernel(const uint8_t *__restrict__ in, T *__restric
         }
         T *dst = out + e0;
         if (vec_ok) {
-            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(vals);
+            __stcs(reinterpret_cast<uint4 *>(dst), *reinterpret_cast<const uint4 *>(vals));      // written once, never re-read here
         } else {
 #pragma unroll
             for (int b = 0; b < ELEMS; b++) dst[b] = vals[b];
