@@ -18,7 +18,7 @@
 // connect a lane's own words, pi_k blocks read a 32-bit window lo[i] : hi[i] from shared memory.  A^-1 is
 // a 4 x 4 array of Q x Q circulants.  Two forms of the dense product:
 //   * LUT (the default): a nibble lookup table in shared memory ("four Russians", code_tables.h:
-//     tm_encoder_lut, 8 ... 128 KB): every nibble of s selects one pre-combined, pre-shifted row of M bits that is
+//     tm_encoder_lut, 8 ... 128 KB; M <= 512: one interleaved copy per codeword of the warp, 64 KB): every nibble of s selects one pre-combined, pre-shifted row of M bits that is
 //     XORed into the codeword's words of p_CC -- one LDS + one LOP3 per word, no branches, no bit scans;
 //   * compact (A/B reference, LABRADOR_LDPC_ENC_TM_FORM=1): the 16 first columns (<= 1 KB); every set bit y of s
 //     XORs the window of the column rotated by y (one funnel shift); bound by the XU pipe (BREV + FLO per bit).
@@ -72,9 +72,12 @@ template <int IMM> __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 
-// words between the rows of consecutive nibble values in shared memory: codes with several codewords per warp get
-// M/32 words of padding so that different values (different codewords of the warp) fall into different banks
-template <int M> __host__ __device__ constexpr int enc_lut_vstride() { return 32 * (M / 32) + (M / 32 < 32 ? M / 32 : 0); }
+// Codes with several codewords per warp (M <= 512) keep one copy of the table per codeword of the warp, interleaved word
+// by word: word w of a row sits at (row * MW + w) * CWW + g for copy g, so the 32 lanes of a warp -- MW words of CWW
+// different rows -- always fall into 32 different banks, whatever values the codewords' nibbles have (64 KB for every
+// M <= 512).  Words between the rows of consecutive nibble values:
+template <int M> __host__ __device__ constexpr int enc_lut_copies() { return M / 32 < 32 ? 32 / (M / 32) : 1; }
+template <int M> __host__ __device__ constexpr int enc_lut_vstride() { return 32 * (M / 32) * enc_lut_copies<M>(); }
 template <int M> __host__ __device__ constexpr int enc_lut_words() { return 16 * enc_lut_vstride<M>(); }
 template <int M> __host__ __device__ constexpr int enc_lut_warps() { return M >= 2048 ? 24 : (M >= 512 ? 16 : 8); }
 
@@ -115,8 +118,18 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
     if constexpr (LUT) {
         const uint4 *src = reinterpret_cast<const uint4 *>(ainv);
         uint4 *dst = reinterpret_cast<uint4 *>(tab);
-        constexpr int ROW4 = 32 * MW / 4, VS4 = enc_lut_vstride<M>() / 4;       // per nibble value, in uint4
-        for (int i = threadIdx.x; i < 16 * ROW4; i += blockDim.x) dst[(i / ROW4) * VS4 + i % ROW4] = src[i];
+        if constexpr (CWW == 1) {
+            for (int i = threadIdx.x; i < TABW / 4; i += blockDim.x) dst[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < 512 * MW / 4; i += blockDim.x) {
+                const uint4 v = src[i];
+                const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int g = 0; g < CWW; g++) tab[(4 * i + k) * CWW + g] = w4[k];
+            }
+        }
     } else {
         for (int i = threadIdx.x; i < 16 * QW; i += blockDim.x) {
             const int qi = i / (4 * QW);
@@ -234,7 +247,7 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
         for (int wi = 0; wi < WPL; wi++) pc[wi] = 0;
         if constexpr (LUT) {
             // Row of the table for (nibble value v, source quarter qj, nibble position nib): byte offset
-            // v * VS + (qj * 8 + nib) * 4 MW (VS = enc_lut_vstride words).  v * VS comes from one LOP3 (the nibble in place inside its byte) and
+            // v * VS + (qj * 8 + nib) * 4 MW CWW (VS = enc_lut_vstride words).  v * VS comes from one LOP3 (the nibble in place inside its byte) and
             // one IMAD whose multiplier is a kernel parameter (keeps it on the FMA pipe); the rest is an immediate.
             const uint32_t tab_sa = (uint32_t)__cvta_generic_to_shared(tab);
 #pragma unroll
@@ -244,7 +257,7 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
                     const uint32_t D = __shfl_sync(kFull, sv[wj], grp * LPC + l);
                     const int j = l + wj * LPC, qj = j / QW, wq = j % QW;
                     // this lane's first word inside a row; its other words follow LPC words apart
-                    const uint32_t a0 = tab_sa + (uint32_t)((qj * 8 * MW + ((wl & ~(QW - 1)) | ((wl - wq) & (QW - 1)))) * 4);
+                    const uint32_t a0 = tab_sa + (uint32_t)(((qj * 8 * MW + ((wl & ~(QW - 1)) | ((wl - wq) & (QW - 1)))) * CWW + grp) * 4);
                     static_for<0, 4>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         const uint32_t Db = __byte_perm(D, 0, 0x4440 + b);
@@ -252,7 +265,7 @@ encode_tm_kernel(const TmParams prm, const uint32_t *__restrict__ ainv, const ui
                         const uint32_t r1 = (Db & 0xF0u) * vs_hi + a0;
                         static_for<0, WPL>([&](auto wii) {
                             constexpr int wi = decltype(wii)::value;
-                            pc[wi] ^= lds_u32<(2 * b) * MW * 4 + wi * LPC * 4>(r0) ^ lds_u32<(2 * b + 1) * MW * 4 + wi * LPC * 4>(r1);
+                            pc[wi] ^= lds_u32<((2 * b) * MW + wi * LPC) * CWW * 4>(r0) ^ lds_u32<((2 * b + 1) * MW + wi * LPC) * CWW * 4>(r1);
                         });
                     });
                 }
