@@ -388,16 +388,32 @@ encode_tc_rot_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__restri
     const unsigned long long in_stride = data_all ? KW * 4ull : KW * 8ull;
     const uint8_t *in_base = data_all ? data_all : cw_all;
 
-    for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < batch;
-         f += (unsigned long long)gridDim.x * blockDim.x) {
+    // TC256: the data of the thread's next codeword is fetched before the current one is encoded (the kernel is otherwise
+    // bound by the latency of these loads; +4 %).  TC512 has no registers to spare for it (it spills and loses 6 %).
+    constexpr bool kPrefetch = KW == 4;
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 nxt[NVEC];
+    if (kPrefetch && vec_ok && f < batch) {
+#pragma unroll
+        for (int i = 0; i < NVEC; i++) nxt[i] = reinterpret_cast<const uint4 *>(in_base + f * in_stride)[i];
+    }
+    for (; f < batch; f += step) {
         const uint8_t *in = in_base + f * in_stride;
         uint8_t *cw = cw_all + f * (KW * 8ull);
         uint32_t d[KW], p[KW];
         if (vec_ok) {
+            if (!kPrefetch) {
+#pragma unroll
+                for (int i = 0; i < NVEC; i++) nxt[i] = reinterpret_cast<const uint4 *>(in)[i];
+            }
 #pragma unroll
             for (int i = 0; i < NVEC; i++) {
-                const uint4 v = reinterpret_cast<const uint4 *>(in)[i];
-                d[4 * i] = v.x; d[4 * i + 1] = v.y; d[4 * i + 2] = v.z; d[4 * i + 3] = v.w;
+                d[4 * i] = nxt[i].x; d[4 * i + 1] = nxt[i].y; d[4 * i + 2] = nxt[i].z; d[4 * i + 3] = nxt[i].w;
+            }
+            if (kPrefetch && f + step < batch) {
+#pragma unroll
+                for (int i = 0; i < NVEC; i++) nxt[i] = reinterpret_cast<const uint4 *>(in_base + (f + step) * in_stride)[i];
             }
         } else {
 #pragma unroll
