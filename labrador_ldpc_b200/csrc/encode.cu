@@ -305,16 +305,19 @@ encode_tc128_pair_kernel(const uint32_t *__restrict__ lut_g, const uint8_t *__re
         }
     };
     const unsigned long long pairs = batch / 2;
-    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < pairs;
-         t += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long step = (unsigned long long)gridDim.x * blockDim.x;
+    auto fetch = [&](unsigned long long t) {                // (A.d0, A.d1, B.d0, B.d1) of codeword pair t
+        if (data_all) return reinterpret_cast<const uint4 *>(data_all)[t];
+        const uint4 a = reinterpret_cast<const uint4 *>(cw_all)[2 * t], b = reinterpret_cast<const uint4 *>(cw_all)[2 * t + 1];
+        return make_uint4(a.x, a.y, b.x, b.y);
+    };
+    unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (t < pairs) nxt = fetch(t);
+    for (; t < pairs; t += step) {
         uint4 *cw = reinterpret_cast<uint4 *>(cw_all) + 2 * t;
-        uint4 d;                                            // (A.d0, A.d1, B.d0, B.d1)
-        if (data_all) {
-            d = reinterpret_cast<const uint4 *>(data_all)[t];
-        } else {
-            const uint4 a = cw[0], b = cw[1];
-            d = make_uint4(a.x, a.y, b.x, b.y);
-        }
+        const uint4 d = nxt;
+        if (t + step < pairs) nxt = fetch(t + step);       // the next pair's data is in flight while this one is encoded
         uint32_t pa0, pa1, pb0, pb1;
         parity_of(d.x, d.y, pa0, pa1);
         parity_of(d.z, d.w, pb0, pb1);
