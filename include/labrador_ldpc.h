@@ -190,7 +190,11 @@ bool labrador_ldpc_decode_bf(enum labrador_ldpc_code code, const uint8_t *input,
                              uint8_t *working, size_t max_iters, size_t *iters_run);
 
 /* Replace labrador_ldpc_decode_ms_{i8,i16,f32,f64}, capi/src/lib.rs:97-127
- * (LDPCCode::decode_ms<T>, src/decoder.rs:347).  llrs: n elements, positive = bit 0. */
+ * (LDPCCode::decode_ms<T>, src/decoder.rs:347).  llrs: n elements, positive = bit 0.
+ * f32 / f64: LLRs must not be NaN.  The reference orders magnitudes with `<` (src/decoder.rs:430-435), which skips
+ * a NaN; the kernels use the hardware minimum, which treats a NaN operand differently, so results for NaN input
+ * are unspecified (every other value, +-inf and +-0 included, follows the reference bit for bit).  The soft front
+ * ends (labrador_ldpc_decode_ms_*_soft_batch) map NaN to 0 before decoding. */
 bool labrador_ldpc_decode_ms_i8(enum labrador_ldpc_code code, const int8_t *llrs, uint8_t *output,
                                 int8_t *working, uint8_t *working_u8, size_t max_iters,
                                 size_t *iters_run);

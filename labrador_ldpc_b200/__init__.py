@@ -206,7 +206,7 @@ class LDPCCode(enum.IntEnum):
         if _nbytes(codeword) * 8 != self.n():
             raise ValueError("codeword must be n bits long")
         if _is_torch(codeword) and codeword.is_cuda:
-            _check(lib.labrador_ldpc_encode_batch(int(self), _ptr(codeword), 1))
+            _check(lib.labrador_ldpc_copy_encode_batch_async(int(self), None, _ptr(codeword), 1, _current_stream(codeword)))
         else:
             lib.labrador_ldpc_encode(int(self), _ptr(codeword))
         return codeword
@@ -217,7 +217,11 @@ class LDPCCode(enum.IntEnum):
             raise ValueError("data must be k bits long")
         if _nbytes(codeword) * 8 != self.n():
             raise ValueError("codeword must be n bits long")
-        _check(lib.labrador_ldpc_copy_encode_batch(int(self), _ptr(data), _ptr(codeword), 1))
+        stream = _current_stream(codeword)
+        if stream is not None:
+            _check(lib.labrador_ldpc_copy_encode_batch_async(int(self), _ptr(data), _ptr(codeword), 1, stream))
+        else:
+            _check(lib.labrador_ldpc_copy_encode_batch(int(self), _ptr(data), _ptr(codeword), 1))
         return codeword
 
     def decode_bf(self, input, output, working=None, maxiters=50):
@@ -233,9 +237,9 @@ class LDPCCode(enum.IntEnum):
         if _is_torch(input) and input.is_cuda:
             okd = _alloc_like(input, (1,), np.uint8)
             itd = _alloc_like(input, (1,), np.uint32)
-            _check(lib.labrador_ldpc_decode_bf_batch(int(self), _ptr(input), _ptr(output), 1, maxiters,
-                                                     _ptr(okd), _ptr(itd)))
-            return bool(okd.item()), int(itd.item())
+            _check(lib.labrador_ldpc_decode_bf_batch_async(int(self), _ptr(input), _ptr(output), 1, maxiters,
+                                                           _ptr(okd), _ptr(itd), _current_stream(input)))
+            return bool(okd.item()), int(itd.item())      # .item() synchronises with the stream the kernel ran on
         _check(lib.labrador_ldpc_decode_bf_batch(int(self), _ptr(input), _ptr(output), 1, maxiters,
                                                  _ptr(ok), _ptr(it)))
         return bool(ok[0]), int(it[0])
@@ -256,7 +260,8 @@ class LDPCCode(enum.IntEnum):
         if _is_torch(llrs) and llrs.is_cuda:
             okd = _alloc_like(llrs, (1,), np.uint8)
             itd = _alloc_like(llrs, (1,), np.uint32)
-            _check(fn(int(self), _ptr(llrs), _ptr(output), 1, maxiters, _ptr(okd), _ptr(itd)))
+            _check(lib.labrador_ldpc_decode_ms_batch_async(int(self), LLR_TYPES[ty], _ptr(llrs), _ptr(output), 1, maxiters,
+                                                           _ptr(okd), _ptr(itd), _current_stream(llrs)))
             return bool(okd.item()), int(itd.item())
         ok = np.zeros(1, np.uint8)
         it = np.zeros(1, np.uint32)
@@ -270,7 +275,11 @@ class LDPCCode(enum.IntEnum):
             raise ValueError("input.len() != n/8")
         if _nbytes(llrs) != self.n() * np.dtype(_NP_OF[ty]).itemsize:
             raise ValueError("llrs.len() != n")
-        _check(getattr(lib, "labrador_ldpc_hard_to_llrs_%s_batch" % ty)(int(self), _ptr(input), _ptr(llrs), 1))
+        stream = _current_stream(llrs)
+        if stream is not None:
+            _check(lib.labrador_ldpc_hard_to_llrs_batch_async(int(self), LLR_TYPES[ty], _ptr(input), _ptr(llrs), 1, stream))
+        else:
+            _check(getattr(lib, "labrador_ldpc_hard_to_llrs_%s_batch" % ty)(int(self), _ptr(input), _ptr(llrs), 1))
         return llrs
 
     def llrs_to_hard(self, llrs, output, ty=None):
@@ -280,7 +289,11 @@ class LDPCCode(enum.IntEnum):
             raise ValueError("llrs.len() != n")
         if _nbytes(output) != self.n() // 8:
             raise ValueError("output.len() != n/8")
-        _check(getattr(lib, "labrador_ldpc_llrs_to_hard_%s_batch" % ty)(int(self), _ptr(llrs), _ptr(output), 1))
+        stream = _current_stream(llrs)
+        if stream is not None:
+            _check(lib.labrador_ldpc_llrs_to_hard_batch_async(int(self), LLR_TYPES[ty], _ptr(llrs), _ptr(output), 1, stream))
+        else:
+            _check(getattr(lib, "labrador_ldpc_llrs_to_hard_%s_batch" % ty)(int(self), _ptr(llrs), _ptr(output), 1))
         return output
 
     # ---- batched API (frame-major [batch][len] buffers) ----
@@ -289,6 +302,12 @@ class LDPCCode(enum.IntEnum):
         if per_frame_bytes == 0 or nb % per_frame_bytes:
             raise ValueError("buffer is not a whole number of frames")
         return nb // per_frame_bytes
+
+    @staticmethod
+    def _check_frames(name, buf, batch, per_frame_bytes):
+        """The C side writes `batch` frames into every result array: a caller-supplied one must hold exactly that."""
+        if buf is not None and _nbytes(buf) != batch * per_frame_bytes:
+            raise ValueError("%s must hold %d frames of %d bytes (has %d bytes)" % (name, batch, per_frame_bytes, _nbytes(buf)))
 
     def copy_encode_batch(self, data, codewords=None, stream=None):
         batch = self._batch_of(data, self.k() // 8)
@@ -305,7 +324,11 @@ class LDPCCode(enum.IntEnum):
 
     def encode_batch(self, codewords):
         batch = self._batch_of(codewords, self.n() // 8)
-        _check(lib.labrador_ldpc_encode_batch(int(self), _ptr(codewords), batch))
+        stream = _current_stream(codewords)
+        if stream is not None:     # data == NULL: in place (csrc/capi.cu encode_impl)
+            _check(lib.labrador_ldpc_copy_encode_batch_async(int(self), None, _ptr(codewords), batch, stream))
+        else:
+            _check(lib.labrador_ldpc_encode_batch(int(self), _ptr(codewords), batch))
         return codewords
 
     def decode_ms_batch(self, llrs, maxiters, output=None, success=None, iters=None, ty=None, stream=None):
@@ -318,8 +341,9 @@ class LDPCCode(enum.IntEnum):
             success = _alloc_like(llrs, (batch,), np.uint8)
         if iters is None:
             iters = _alloc_like(llrs, (batch,), np.uint32)
-        if self._batch_of(output, self.output_len()) != batch:
-            raise ValueError("output has the wrong number of frames")
+        self._check_frames("output", output, batch, self.output_len())
+        self._check_frames("success", success, batch, 1)
+        self._check_frames("iters", iters, batch, 4)
         stream = stream if stream is not None else _current_stream(llrs)
         if stream is not None:
             _check(lib.labrador_ldpc_decode_ms_batch_async(int(self), LLR_TYPES[ty], _ptr(llrs), _ptr(output), batch,
@@ -337,8 +361,9 @@ class LDPCCode(enum.IntEnum):
             success = _alloc_like(src, (batch,), np.uint8)
         if iters is None:
             iters = _alloc_like(src, (batch,), np.uint32)
-        if self._batch_of(output, self.output_len()) != batch:
-            raise ValueError("output has the wrong number of frames")
+        self._check_frames("output", output, batch, self.output_len())
+        self._check_frames("success", success, batch, 1)
+        self._check_frames("iters", iters, batch, 4)
         stream = stream if stream is not None else _current_stream(src)
         if stream is not None:
             _check(lib.labrador_ldpc_decode_ms_front_batch_async(
@@ -375,6 +400,7 @@ class LDPCCode(enum.IntEnum):
         batch = self._batch_of(soft, self.n() * 4)
         if llrs is None:
             llrs = _alloc_like(soft, (batch, self.n()), _NP_OF[ty])
+        self._check_frames("llrs", llrs, batch, self.n() * np.dtype(_NP_OF[ty]).itemsize)
         stream = stream if stream is not None else _current_stream(soft)
         if stream is not None:
             _check(lib.labrador_ldpc_quantise_batch_async(int(self), LLR_TYPES[ty], _ptr(soft), float(scale), int(limit),
@@ -400,6 +426,7 @@ class LDPCCode(enum.IntEnum):
         batch = self._batch_of(codewords, self.n() // 8)
         if out is None:
             out = _alloc_like(codewords, (batch, self.n()), _NP_OF[ty])
+        self._check_frames("out", out, batch, self.n() * np.dtype(_NP_OF[ty]).itemsize)
         stream = _current_stream(codewords)
         if stream is not None:
             _check(lib.labrador_ldpc_awgn_batch_async(int(self), LLR_TYPES[ty], _ptr(codewords), float(sigma), float(scale),
@@ -416,6 +443,7 @@ class LDPCCode(enum.IntEnum):
             raise ValueError("decoded has the wrong number of frames")
         if errors is None:
             errors = _alloc_like(data, (batch,), np.uint32)
+        self._check_frames("errors", errors, batch, 4)
         stream = _current_stream(data)
         if stream is not None:
             _check(lib.labrador_ldpc_count_errors_batch_async(int(self), _ptr(decoded), _ptr(data), _ptr(errors), batch, stream))
@@ -431,6 +459,9 @@ class LDPCCode(enum.IntEnum):
             success = _alloc_like(input, (batch,), np.uint8)
         if iters is None:
             iters = _alloc_like(input, (batch,), np.uint32)
+        self._check_frames("output", output, batch, self.output_len())
+        self._check_frames("success", success, batch, 1)
+        self._check_frames("iters", iters, batch, 4)
         stream = stream if stream is not None else _current_stream(input)
         if stream is not None:
             _check(lib.labrador_ldpc_decode_bf_batch_async(int(self), _ptr(input), _ptr(output), batch, maxiters,
@@ -444,6 +475,7 @@ class LDPCCode(enum.IntEnum):
         batch = self._batch_of(input, self.n() // 8)
         if llrs is None:
             llrs = _alloc_like(input, (batch, self.n()), _NP_OF[ty])
+        self._check_frames("llrs", llrs, batch, self.n() * np.dtype(_NP_OF[ty]).itemsize)
         stream = stream if stream is not None else _current_stream(input)
         if stream is not None:
             _check(lib.labrador_ldpc_hard_to_llrs_batch_async(int(self), LLR_TYPES[ty], _ptr(input), _ptr(llrs),
@@ -457,6 +489,7 @@ class LDPCCode(enum.IntEnum):
         batch = self._batch_of(llrs, self.n() * np.dtype(_NP_OF[ty]).itemsize)
         if output is None:
             output = _alloc_like(llrs, (batch, self.n() // 8), np.uint8)
+        self._check_frames("output", output, batch, self.n() // 8)
         stream = stream if stream is not None else _current_stream(llrs)
         if stream is not None:
             _check(lib.labrador_ldpc_llrs_to_hard_batch_async(int(self), LLR_TYPES[ty], _ptr(llrs), _ptr(output),

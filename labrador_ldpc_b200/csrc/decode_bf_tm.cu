@@ -279,11 +279,11 @@ cudaError_t launch_bf_tm(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
     constexpr int MW = M / 32, CWW = MW < 32 ? 32 / MW : 1;            // codewords per warp
     const size_t smem = (size_t)kBfWarps * CWW * bf_cw_stride<P, M>() * sizeof(uint32_t);
     auto kern = decode_bf_tm_kernel<RATE, M>;
-    static bool configured[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[ctx.device & 15] = true;
+        configured[ctx.device] = true;
     }
     int per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kBfWarps, smem);
@@ -297,9 +297,9 @@ cudaError_t launch_bf_tm(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
     const unsigned long long per_cta = (unsigned long long)kBfWarps * claim;
     const unsigned long long need = (groups + per_cta - 1) / per_cta;
     if (grid > need) grid = need;
-    unsigned long long *counter = nullptr;
-    e = next_counter(ctx.device, stream, &counter);
-    if (e != cudaSuccess) return e;
+    WorkCounter wc(ctx, stream);
+    if (wc.error() != cudaSuccess) return wc.error();
+    unsigned long long *counter = wc.ptr();
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kBfWarps, smem, stream>>>(prm, input, output, (unsigned long long)batch, mi, success,
                                                           iters, counter, (int)claim);

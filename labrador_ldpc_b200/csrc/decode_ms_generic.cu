@@ -193,6 +193,11 @@ cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *
             ctx.vscratch_bytes = need;
         }
         scratch = static_cast<T *>(ctx.vscratch);
+        // the slots are shared by every launch that needs them: order this one behind the previous user, whatever
+        // stream that ran on (as decode_bf_tc.cu does for its retry list)
+        if (ctx.vscratch_done) err = cudaStreamWaitEvent(stream, ctx.vscratch_done, 0);
+        else err = cudaEventCreateWithFlags(&ctx.vscratch_done, cudaEventDisableTiming);
+        if (err != cudaSuccess) return err;
     }
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
@@ -200,6 +205,7 @@ cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *
                                                           output, (unsigned long long)batch, mi, success, iters, scratch,
                                                           front.scale, front.limit);
     count_launch();
+    if (scratch) cudaEventRecord(ctx.vscratch_done, stream);
     return cudaGetLastError();
 }
 

@@ -28,7 +28,6 @@
 #include "tc_common.cuh"
 
 namespace ldpc {
-namespace tm { cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **out); }
 
 namespace {
 
@@ -265,11 +264,11 @@ cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     const size_t warp_bytes = ((sizeof(typename MsgStore<T>::type) * CWW * tc_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kWarpsPerCta;
     auto kern = decode_ms_tc_kernel<M, T, FRONT>;
-    static bool configured[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[ctx.device & 15] = true;
+        configured[ctx.device] = true;
     }
     int per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kWarpsPerCta, smem);
@@ -279,9 +278,9 @@ cudaError_t launch_tc(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
     const unsigned long long need = (groups + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
-    unsigned long long *counter = nullptr;
-    e = tm::next_counter(ctx.device, stream, &counter);
-    if (e != cudaSuccess) return e;
+    WorkCounter wc(ctx, stream);
+    if (wc.error() != cudaSuccess) return wc.error();
+    unsigned long long *counter = wc.ptr();
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kWarpsPerCta, smem, stream>>>(
         static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs), output, (unsigned long long)batch, mi, success,

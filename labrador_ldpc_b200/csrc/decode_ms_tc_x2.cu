@@ -22,7 +22,6 @@
 #include "tc_common.cuh"
 
 namespace ldpc {
-namespace tm { cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **out); }
 
 namespace {
 
@@ -230,24 +229,24 @@ cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     const size_t warp_bytes = ((4u * CWW * x2_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kX2Warps;
     auto kern = decode_ms_tc_i8x2_kernel<M, FRONT>;
-    static bool configured[16] = {};
-    static int per_sm_cached[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    static int per_sm_cached[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * kX2Warps, smem);
         if (e != cudaSuccess) return e;
-        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
-        configured[ctx.device & 15] = true;
+        per_sm_cached[ctx.device] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device] = true;
     }
     const unsigned long long groups = (batch + 2 * CWW - 1) / (2 * CWW);
-    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device];
     const unsigned long long need = (groups + kX2Warps - 1) / kX2Warps;
     if (grid > need) grid = need;
-    unsigned long long *counter = nullptr;
-    cudaError_t e = tm::next_counter(ctx.device, stream, &counter);
-    if (e != cudaSuccess) return e;
+    WorkCounter wc(ctx, stream);
+    if (wc.error() != cudaSuccess) return wc.error();
+    unsigned long long *counter = wc.ptr();
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kX2Warps, smem, stream>>>(
         static_cast<const typename FrontSrc<FRONT, int8_t>::type *>(llrs), output, (unsigned long long)batch, mi,

@@ -41,6 +41,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -49,29 +50,6 @@
 #include "tm_common.cuh"
 
 namespace ldpc {
-namespace tm {
-
-struct Counters {
-    unsigned long long *ring = nullptr;
-    int next = 0;
-    int device = -1;
-};
-constexpr int kCounterRing = 1024;
-Counters g_counters[16];
-
-cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **out) {
-    Counters *cs = &g_counters[device & 15];   // launchers run under the per-device context mutex
-    if (cs->device < 0) {
-        cudaError_t e = cudaMalloc(&cs->ring, kCounterRing * sizeof(unsigned long long));
-        if (e != cudaSuccess) return e;
-        cs->device = device;
-    }
-    *out = cs->ring + cs->next;
-    cs->next = (cs->next + 1) % kCounterRing;
-    return cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream);
-}
-
-}  // namespace tm
 
 using namespace tm;
 
@@ -169,6 +147,61 @@ __device__ __forceinline__ void min_excluding_self3(const uint32_t (&a)[kMaxDeg]
     if constexpr (ODD) mu[DC - 1] = pre;
 }
 
+// The same on fp16 lanes: a lane holding the signed integer d (|d| < 1024) as a sign-magnitude subnormal (bit 15 = sign,
+// low bits = |d|).  HMNMX2 / VHMNMX take |.| as a free operand modifier, so no separate absolute value is needed, and the
+// result (a non-negative subnormal) is bit-identical to the integer |d|.  TWO_ONLY: 2-input minima only (3*DC-6 full-rate
+// HMNMX2) instead of the 2*DC-2 mix with the three-input VHMNMX.
+__device__ __forceinline__ uint32_t hmin2a(uint32_t x, uint32_t y) { return h2u(__hmin2(__habs2(u2h(x)), __habs2(u2h(y)))); }
+__device__ __forceinline__ uint32_t hmin3a(uint32_t x, uint32_t y, uint32_t z) {
+    return h2u(__hmin2(__hmin2(__habs2(u2h(x)), __habs2(u2h(y))), __habs2(u2h(z))));
+}
+template <int DC, bool TWO_ONLY>
+__device__ __forceinline__ void min_excluding_self_h(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
+    static_assert(DC >= 3, "every output must come out of a minimum (which applies the absolute value)");
+    if constexpr (TWO_ONLY) {
+        uint32_t suf[kMaxDeg];
+        suf[DC - 1] = a[DC - 1];
+#pragma unroll
+        for (int k = DC - 2; k >= 1; k--) suf[k] = hmin2a(a[k], suf[k + 1]);
+        uint32_t pre = a[0];
+        mu[0] = suf[1];
+#pragma unroll
+        for (int k = 1; k < DC - 1; k++) {
+            mu[k] = hmin2a(pre, suf[k + 1]);
+            pre = hmin2a(pre, a[k]);
+        }
+        mu[DC - 1] = pre;
+    } else {
+        constexpr int NPAIR = DC / 2;
+        constexpr bool ODD = (DC & 1) != 0;
+        uint32_t suf[kMaxDeg / 2 + 2];
+        if constexpr (ODD) suf[NPAIR] = a[DC - 1];
+#pragma unroll
+        for (int j = NPAIR - 1; j >= 1; j--) {
+            if (j == NPAIR - 1 && !ODD) suf[j] = hmin2a(a[2 * j], a[2 * j + 1]);
+            else suf[j] = hmin3a(a[2 * j], a[2 * j + 1], suf[j + 1]);
+        }
+        uint32_t pre = 0;
+#pragma unroll
+        for (int j = 0; j < NPAIR; j++) {
+            const bool has_pre = j > 0, has_suf = (j + 1 < NPAIR) || ODD;
+            if (has_pre && has_suf) {
+                mu[2 * j] = hmin3a(pre, a[2 * j + 1], suf[j + 1]);
+                mu[2 * j + 1] = hmin3a(pre, a[2 * j], suf[j + 1]);
+            } else if (has_suf) {
+                mu[2 * j] = hmin2a(a[2 * j + 1], suf[j + 1]);
+                mu[2 * j + 1] = hmin2a(a[2 * j], suf[j + 1]);
+            } else {
+                mu[2 * j] = hmin2a(pre, a[2 * j + 1]);
+                mu[2 * j + 1] = hmin2a(pre, a[2 * j]);
+            }
+            if (j + 1 < NPAIR || ODD)
+                pre = has_pre ? hmin3a(pre, a[2 * j], a[2 * j + 1]) : hmin2a(a[2 * j], a[2 * j + 1]);
+        }
+        if constexpr (ODD) mu[DC - 1] = pre;
+    }
+}
+
 template <int DC, bool SUF_F, bool PRE_F, bool COMB_F>
 __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg], uint32_t (&mu)[kMaxDeg]) {
     uint32_t suf[kMaxDeg];
@@ -189,20 +222,25 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 //   ARITH 1: integer lanes throughout (VIADDMNMX chain, two's-complement u)      -- ALU-pipe bound
 //   ARITH 3: ARITH 1 with |v| by VABSDIFF4 (no +127 offset to carry around)
 //   ARITH 5: ARITH 3 with the three-input minimum (2*DC-2 instead of 3*DC-6 minima per check word)
+//   ARITH 6: ARITH 5 with |v| and the minima on fp16 lanes: d = C - 127 by one HADD2 (FMA pipe) instead of VABSDIFF4,
+//            |d| as the free operand modifier of HMNMX2 / VHMNMX (KNOBS bit 4: two-input minima only)
+//   ARITH 7: ARITH 6 with the sign-magnitude u of ARITH 4
 //   ARITH 4: ARITH 3 with u sent in sign-magnitude (1 LOP3 + 1 IMAD on the check side) and converted to
 //            two's complement on the FMA pipe by the variable side (fp16 magic-constant add); KNOBS as ARITH 2
 //   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
 //            part of the minima on the FMA pipe (bits of KNOBS: 1 cv-min, 2 suffix, 4 prefix, 8 combine)
 // FRONT (front.cuh): what a frame of `llrs_all` holds -- n int8 LLRs, n float soft values quantised on load,
 // or n/8 bytes of hard decisions; the frame is staged in shared memory by the same bulk copy in every case.
-template <int RATE, int M, int WPT, int ARITH, int KNOBS, int MINB = 1, int FRONT = kFrontNone>
+// PROF (development aid, tools/tm_phase_prof.py): every warp accumulates the clock cycles it spends in the variable
+// phase, at the barrier after it, in the check phase and in the exit test (incl. its barriers) into prof[warp][4].
+template <int RATE, int M, int WPT, int ARITH, int KNOBS, int MINB = 1, int FRONT = kFrontNone, bool PROF = false>
 __global__ void __launch_bounds__(M / 2 / WPT, MINB)
 decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
                        uint8_t *__restrict__ out_all,
                        unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                        uint32_t *__restrict__ iters_out, unsigned long long *__restrict__ counter,
                        const uint32_t one /* == 1: keeps the borrow-free subtractions on the FMA pipe (IMAD) */,
-                       const float fscale, const float flimit) {
+                       const float fscale, const float flimit, unsigned long long *__restrict__ prof) {
     typedef typename FrontSrc<FRONT, int8_t>::type Src;
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
@@ -264,6 +302,13 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
         hbw[wi] = (uint32_t)(((wd / S) * Q + (wd % S)) >> 5);
     }
     const uint32_t c254 = 0x00fe00feu * one, c255 = 0x00ff00ffu * one, c256 = one << 8;
+    // KNOBS bit 5: in-thread row-0 exit test.  Row 0 is I(CA) + I(CP) + P(CP).  The two identity terms of a check belong
+    // to the thread that owns the check; the marginal of the permuted term travels in the spare high byte of that block's
+    // message (one IMAD on the variable side), so every thread tests its own row-0 checks while it processes them: no
+    // ballots, no hard-bit words and no serial syndrome pass per iteration.  The marginals of all columns are kept as
+    // bytes (two columns per register, one PRMT per pair) for the rare second stage and for the output.
+    constexpr bool PIGGY = (KNOBS & 32) != 0;
+    constexpr int NG = (NCOL + 1) / 2;     // PIGGY: registers of gathered marginal bytes per word slot
     constexpr bool CV_F = (KNOBS & 1) != 0, SUF_F = (KNOBS & 2) != 0, PRE_F = (KNOBS & 4) != 0, COMB_F = (KNOBS & 8) != 0;
 
     // Frames are claimed one ahead: while frame f is decoded, the LLRs of the next claimed frame are
@@ -279,6 +324,14 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
     }
     __syncthreads();
     unsigned cur = 0, bar_parity = 0;    // bit b of bar_parity = phase parity of s_bar[b]
+    unsigned pf_var = 0, pf_bar = 0, pf_chk = 0, pf_exit = 0, pf_t = 0;
+    auto pf_lap = [&](unsigned &acc) {
+        if constexpr (PROF) {
+            const unsigned now = (unsigned)clock();
+            acc += now - pf_t;
+            pf_t = now;
+        }
+    };
 
     for (;;) {
         const unsigned long long frame = s_frame[cur];
@@ -329,11 +382,26 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
         unsigned iters_run = max_iters;
         bool ok = false;
         uint32_t pack[WPT];           // hard bits of the columns not covered by stage 1
+        uint32_t gat[PIGGY ? NG : 1][WPT];   // PIGGY: biased marginals as bytes: column 2j in bytes 0 / 2, column 2j+1 in bytes 1 / 3
+        uint32_t hloc8[WPT], bad[WPT];       // PIGGY: bit 15 / 31 = XOR of the two in-thread terms; row-0 checks that failed
         bool hb_complete = true;      // hb[] holds every column's hard bits of the latest variable phase
         // ballot-packs the deferred columns' hard bits into hb[] (stage 2 / final output)
         auto flush_pack = [&]() {
 #pragma unroll
             for (int wi = 0; wi < WPT; wi++) {
+                if constexpr (PIGGY) {
+                    static_for<0, NCOL>([&](auto ci) {
+                        constexpr int c = decltype(ci)::value;
+                        const uint32_t g = gat[c / 2][wi] >> ((c & 1) * 8);             // bit 7 / 23: marginal >= 0
+                        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (g & 0x00000080u) == 0);
+                        const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (g & 0x00800000u) == 0);
+                        if (lane == 0) {
+                            hb[hbw[wi] + c * M / 32] = b0;
+                            hb[hbw[wi] + (c * M + S) / 32] = b1;
+                        }
+                    });
+                    continue;
+                }
                 int kpos = 0;
                 static_for<0, NCOL>([&](auto ci) {
                     constexpr int c = NCOL - 1 - decltype(ci)::value;     // last packed column sits at bit 7 / 23
@@ -351,6 +419,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
         };
         for (unsigned iter = 0; iter < max_iters; iter++) {
             // ================= variable phase (:382-411 and :421) =================
+            if constexpr (PROF) pf_t = (unsigned)clock();
 #pragma unroll
             for (int wi = 0; wi < WPT; wi++) {
                 pack[wi] = 0;
@@ -369,7 +438,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             } else {
                                 u = idm[count_i<P>(b)][wi];
                             }
-                            if constexpr (ARITH == 4) {
+                            if constexpr (ARITH == 4 || ARITH == 7) {
                                 // sign-magnitude (fp16 subnormal +-mu) -> two's complement, on the FMA pipe only:
                                 // +-mu*2^-24 + 1.5*2^-14 has the bit pattern 0x0600 +- mu; then subtract 0x0600 per lane
                                 u = __vadd2(h2u(__hadd2(u2h(u), u2h(0x06000600u))), 0xFA00FA00u);
@@ -394,7 +463,12 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                         va = f_sub(0x00ff00ffu, van);
                     }
                     // hard decisions of the marginals: va < 0  <=>  VA < 128  <=>  bit 7 clear
-                    if constexpr (c == CA || c == CP) {
+                    if constexpr (PIGGY) {
+                        if constexpr ((c & 1) == 0) gat[c / 2][wi] = va;               // bytes 1 / 3 are zero
+                        else gat[c / 2][wi] = __byte_perm(gat[c / 2][wi], va, 0x6240);
+                        if constexpr (c == CA) hloc8[wi] = va;
+                        if constexpr (c == CP) hloc8[wi] = (hloc8[wi] ^ va) * c256;     // bit 15 / 31, no carry between the lanes
+                    } else if constexpr (c == CA || c == CP) {
                         const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (va & 0x00000080u) == 0);
                         const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (va & 0x00800000u) == 0);
                         if (lane == 0) {
@@ -412,6 +486,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             uint32_t cv;
                             if constexpr (ARITH != 2) cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
                             else cv = pmin<CV_F>(f_relu_add(van, ub[k]), 0x00fe00feu);
+                            if constexpr (PIGGY && b == 2) cv = va * c256 + cv;          // high byte: the biased marginal
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
                                 msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
@@ -422,7 +497,9 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                     });
                 });
             }
+            pf_lap(pf_var);
             __syncthreads();
+            pf_lap(pf_bar);
 
             // ================= check phase (:391-405 and :422-447) =================
 #pragma unroll
@@ -440,6 +517,11 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             uint32_t cv;
                             if constexpr (P::blk(b).isp) cv = msg[count_p<P>(b) * (M / 2) + wd];
                             else cv = idm[count_i<P>(b)][wi];
+                            if constexpr (PIGGY && b == 2) {
+                                // three marginals of this check: (biased bit 7 of each) XORed = NOT the parity of the hard bits
+                                bad[wi] = ~(hloc8[wi] ^ cv) & 0x80008000u;
+                                cv &= 0x00ff00ffu;
+                            }
                             const uint32_t old = cc[b][wi];
                             const uint32_t x = (cv ^ old) & (cv ^ (old + 0x00010001u));   // bit 7: sign flipped and old != 0
                             const uint32_t km = prmt_sign7(x);
@@ -447,11 +529,14 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             cc[b][wi] = cor;
                             ck[k] = cor;
                             if constexpr (ARITH == 1) a[k] = __vmaxu2(cor, c254 * one - cor);    // |v| + 127
+                            else if constexpr (ARITH == 6 || ARITH == 7)
+                                a[k] = h2u(__hsub2(u2h(cor), u2h(0x007f007fu)));                 // -v as a signed fp16 lane
                             else a[k] = __vabsdiffu4(cor, 0x007f007fu);                          // |v|
                             sx ^= cor;                                                     // bit 7: product of signs
                         }
                     });
                     if constexpr (ARITH == 5) min_excluding_self3<DC>(a, mu);
+                    else if constexpr (ARITH == 6 || ARITH == 7) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
                     else if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
                     else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
@@ -463,7 +548,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                                 const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
                                 const uint32_t kk = __vadd2(nm, 0xff81ff81u);              // -127 or -128
                                 u = __vadd2(mu[k], kk) ^ nm;                               // +-(mu - 127), two's complement
-                            } else if constexpr (ARITH == 3 || ARITH == 5) {
+                            } else if constexpr (ARITH == 3 || ARITH == 5 || ARITH == 6) {
                                 const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
                                 u = __vadd2(mu[k], nm) ^ nm;                               // +-mu, two's complement
                             } else {
@@ -476,6 +561,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                     });
                 });
             }
+            pf_lap(pf_chk);
             // ---- parity of the marginals' hard bits (:445-453), one thread per 32 checks ----
             auto syndrome_word = [&](int sw) {
                 uint32_t synd = 0;
@@ -500,9 +586,14 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
             };
             // stage 1: row 0 only (its hard bits were packed in this iteration's variable phase)
             uint32_t synd = 0;
-            // (done by the HIGHEST-numbered warps: the SM's arbiter favours high warp ids, so the warps with the
-            //  extra work are the ones that reach the barrier early anyway)
-            if (tid >= NT - M / 32) synd = syndrome_word(tid - (NT - M / 32));
+            if constexpr (PIGGY) {
+#pragma unroll
+                for (int wi = 0; wi < WPT; wi++) synd |= bad[wi];
+            } else {
+                // (done by the HIGHEST-numbered warps: the SM's arbiter favours high warp ids, so the warps with the
+                //  extra work are the ones that reach the barrier early anyway)
+                if (tid >= NT - M / 32) synd = syndrome_word(tid - (NT - M / 32));
+            }
             hb_complete = false;
             if (__syncthreads_or(synd != 0) == 0) {
                 // stage 2: row 0 is clean -- pack the other columns and test rows 1..NROW-1
@@ -517,6 +608,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                     break;
                 }
             }
+            pf_lap(pf_exit);
         }
         if (!hb_complete) {       // decoding failed: the output is the hard decision of the last marginals (:466-473)
             flush_pack();
@@ -542,9 +634,18 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
         __syncthreads();   // hb / msg / stage / s_frame are reused by the next frame
         cur ^= 1;
     }
+    if constexpr (PROF) {
+        if (lane == 0) {
+            unsigned long long *pw = prof + (tid >> 5) * 4;
+            atomicAdd(pw + 0, (unsigned long long)pf_var);
+            atomicAdd(pw + 1, (unsigned long long)pf_bar);
+            atomicAdd(pw + 2, (unsigned long long)pf_chk);
+            atomicAdd(pw + 3, (unsigned long long)pf_exit);
+        }
+    }
 }
 
-template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1, int MINB = 1, int FRONT = kFrontNone>
+template <int RATE, int M, int WPT, int ARITH = 2, int KNOBS = 2 + 1, int MINB = 1, int FRONT = kFrontNone, bool PROF = false>
 cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
                       const Front &front = Front()) {
@@ -554,27 +655,45 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
     const TmParams prm = make_params<RATE>(c);
     const size_t smem = ((size_t)NP * (M / 2) + (((size_t)P::NCOL * M / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) +
                         2 * front_frame_bytes(front, (P::NCOL - 1) * M, kI8);   // messages + hard bits + two input staging buffers
-    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS, MINB, FRONT>;
-    static bool configured[16] = {};
-    if (!configured[ctx.device & 15]) {
+    auto kern = decode_ms_tm_i8_kernel<RATE, M, WPT, ARITH, KNOBS, MINB, FRONT, PROF>;
+    static bool configured[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[ctx.device & 15] = true;
+        configured[ctx.device] = true;
     }
     int per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    static const int cap = [] { const char *e = getenv("LABRADOR_LDPC_TM_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+    if (cap > 0 && per_sm > cap) per_sm = cap;     // A/B runs: fewer resident CTAs than fit
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
     if (grid > batch) grid = batch;
-    unsigned long long *counter = nullptr;
-    e = next_counter(ctx.device, stream, &counter);
-    if (e != cudaSuccess) return e;
+    WorkCounter wc(ctx, stream);
+    if (wc.error() != cudaSuccess) return wc.error();
+    unsigned long long *counter = wc.ptr();
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
+    unsigned long long *prof = nullptr;
+    if constexpr (PROF) {
+        e = cudaMalloc(&prof, 32 * 4 * sizeof(unsigned long long));
+        if (e != cudaSuccess) return e;
+        cudaMemsetAsync(prof, 0, 32 * 4 * sizeof(unsigned long long), stream);
+    }
     kern<<<(unsigned)grid, NT, smem, stream>>>(prm, static_cast<const typename FrontSrc<FRONT, int8_t>::type *>(llrs), output,
                                                (unsigned long long)batch, mi, success, iters, counter, 1u, front.scale,
-                                               front.limit);
+                                               front.limit, prof);
     count_launch();
+    if constexpr (PROF) {     // development aid: per-warp cycle totals of the four parts of an iteration, to stderr
+        unsigned long long h[32 * 4];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(prof);
+        fprintf(stderr, "tm_prof arith=%d knobs=%d grid=%llu threads=%d batch=%zu\n", ARITH, KNOBS, grid, NT, batch);
+        for (int w = 0; w < NT / 32; w++)
+            fprintf(stderr, "tm_prof warp %2d var %llu bar %llu chk %llu exit %llu\n", w, h[w * 4], h[w * 4 + 1], h[w * 4 + 2],
+                    h[w * 4 + 3]);
+    }
     return cudaGetLastError();
 }
 
@@ -591,6 +710,21 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if constexpr (M == 2048) {   // TM8192: 2 words per thread (512 threads x <=128 registers) is also compiled
         static const int wpt = [] { const char *e = getenv("LABRADOR_LDPC_TM_WPT"); return e ? atoi(e) : 2; }();
         if (wpt == 2) {
+            static const bool prof = [] { const char *e = getenv("LABRADOR_LDPC_TM_PROF"); return e && atoi(e) != 0; }();
+            if (prof) {
+                if (arith == 2) return launch_tm<RATE, M, 2, 2, 6, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                if (arith == 4) return launch_tm<RATE, M, 2, 4, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                if (arith == 6) return launch_tm<RATE, M, 2, 6, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                if (arith == 7) return launch_tm<RATE, M, 2, 7, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                if (arith == 632) return launch_tm<RATE, M, 2, 6, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                return launch_tm<RATE, M, 2, 5, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            }
+            if (arith == 6) return launch_tm<RATE, M, 2, 6, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 632) return launch_tm<RATE, M, 2, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 532) return launch_tm<RATE, M, 2, 5, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 616) return launch_tm<RATE, M, 2, 6, 16>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 7) return launch_tm<RATE, M, 2, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 716) return launch_tm<RATE, M, 2, 7, 16>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 3) return launch_tm<RATE, M, 2, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 5) return launch_tm<RATE, M, 2, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 4) return launch_tm<RATE, M, 2, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -600,6 +734,9 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 1) return launch_tm<RATE, M, 1, 1, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 3) return launch_tm<RATE, M, 1, 3, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 5) return launch_tm<RATE, M, 1, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 6) return launch_tm<RATE, M, 1, 6, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 632) return launch_tm<RATE, M, 1, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 7) return launch_tm<RATE, M, 1, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
         if (arith == 52) return launch_tm<RATE, M, 1, 5, 0, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     }

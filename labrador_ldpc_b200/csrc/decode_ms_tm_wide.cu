@@ -367,11 +367,11 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
         if constexpr (std::is_same<T, double>::value) return &decode_ms_tm_wide_kernel_allregs<RATE, M, T, NT, FRONT>;
         else return &decode_ms_tm_wide_kernel<RATE, M, T, NT, FRONT>;
     }();
-    static bool configured[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[ctx.device & 15] = true;
+        configured[ctx.device] = true;
     }
     int per_sm = 1;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
@@ -379,9 +379,9 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
     if (per_sm < 1) per_sm = 1;
     unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm;
     if (grid > batch) grid = batch;
-    unsigned long long *counter = nullptr;
-    e = next_counter(ctx.device, stream, &counter);
-    if (e != cudaSuccess) return e;
+    WorkCounter wc(ctx, stream);
+    if (wc.error() != cudaSuccess) return wc.error();
+    unsigned long long *counter = wc.ptr();
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, NT, smem, stream>>>(prm, static_cast<const typename FrontSrc<FRONT, T>::type *>(llrs), output,
                                                (unsigned long long)batch, mi, success, iters, counter, front.scale,

@@ -251,18 +251,18 @@ cudaError_t launch_encode_tc_lut(DeviceCtx &ctx, const DeviceCode &dc, const uin
     constexpr int threads = 512;
     const size_t smem = (size_t)(KW * 32 / GB) * (1 << GB) * KW * 4;
     auto kern = encode_tc_lut_kernel<KW, GB>;
-    static bool configured[16] = {};
-    static int per_sm_cached[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    static int per_sm_cached[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
         if (e != cudaSuccess) return e;
-        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
-        configured[ctx.device & 15] = true;
+        per_sm_cached[ctx.device] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device] = true;
     }
-    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device];
     const unsigned long long need = (batch + threads - 1) / threads;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, KW * 4u);
@@ -337,16 +337,16 @@ cudaError_t launch_encode_tc128_pair(DeviceCtx &ctx, const DeviceCode &dc, const
                                      size_t batch, cudaStream_t stream) {
     constexpr int threads = 512;
     const size_t smem = 16 * 16 * 2 * 4;
-    static bool configured[16] = {};
-    static int per_sm_cached[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    static int per_sm_cached[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         int per_sm = 1;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tc128_pair_kernel, threads, smem);
         if (e != cudaSuccess) return e;
-        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
-        configured[ctx.device & 15] = true;
+        per_sm_cached[ctx.device] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device] = true;
     }
-    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device];
     const unsigned long long need = (batch / 2 + threads - 1) / threads;
     if (grid > need) grid = need;
     if (grid == 0) grid = 1;
@@ -477,18 +477,18 @@ cudaError_t launch_encode_tc_rot_r(DeviceCtx &ctx, const DeviceCode &dc, const u
     constexpr int threads = R > 1 ? 1024 : 512;
     const size_t smem = (size_t)4 * 256 * KW * 4 * R;
     auto kern = encode_tc_rot_kernel<KW, R>;
-    static bool configured[16] = {};
-    static int per_sm_cached[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    static int per_sm_cached[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
         if (e != cudaSuccess) return e;
-        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
-        configured[ctx.device & 15] = true;
+        per_sm_cached[ctx.device] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device] = true;
     }
-    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device];
     const unsigned long long need = (batch + threads - 1) / threads;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, threads, smem, stream>>>(dc.enc_tc_lut, data, codewords, (unsigned long long)batch, KW * 4u * R);

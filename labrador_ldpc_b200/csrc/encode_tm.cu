@@ -339,18 +339,18 @@ cudaError_t launch_enc_tm_form(DeviceCtx &ctx, const CodeInfo &c, const DeviceCo
     constexpr int tabw = LUT ? enc_lut_words<M>() : enc_tab_words<M>();
     const size_t smem = ((size_t)tabw + (size_t)warps * CWW * enc_cw_stride<P, M>()) * sizeof(uint32_t);
     auto kern = encode_tm_kernel<RATE, M, LUT>;
-    static bool configured[16] = {};
-    static int per_sm_cached[16] = {};
-    if (!configured[ctx.device & 15]) {
+    static bool configured[kMaxDevices] = {};
+    static int per_sm_cached[kMaxDevices] = {};
+    if (!configured[ctx.device]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * warps, smem);
         if (e != cudaSuccess) return e;
-        per_sm_cached[ctx.device & 15] = per_sm < 1 ? 1 : per_sm;
-        configured[ctx.device & 15] = true;
+        per_sm_cached[ctx.device] = per_sm < 1 ? 1 : per_sm;
+        configured[ctx.device] = true;
     }
-    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device & 15];
+    unsigned long long grid = (unsigned long long)ctx.sm_count * per_sm_cached[ctx.device];
     const unsigned long long groups = (batch + CWW - 1) / CWW;
     const unsigned long long need = (groups + warps - 1) / warps;
     if (grid > need) grid = need;

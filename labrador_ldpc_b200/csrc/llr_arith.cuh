@@ -78,7 +78,8 @@ template <> struct Arith<float> {
     __device__ static __forceinline__ float maxval() { return FLT_MAX; }
     // fabsf clears the sign bit exactly like the reference's mask (:60-63) and folds into an operand modifier
     __device__ static __forceinline__ float abs(float x) { return fabsf(x); }
-    // a < b ? a : b for the minima over |v| (never NaN, never -0): one FMNMX instead of FSETP + FSEL
+    // a < b ? a : b for the minima over |v| (never -0; NaN LLRs are outside the contract, include/labrador_ldpc.h):
+    // one FMNMX instead of FSETP + FSEL
     __device__ static __forceinline__ float min(float a, float b) { return fminf(a, b); }
     __device__ static __forceinline__ float sat_add(float a, float b) { return __fadd_rn(a, b); }
     __device__ static __forceinline__ float sat_sub(float a, float b) { return __fsub_rn(a, b); }

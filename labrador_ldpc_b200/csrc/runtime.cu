@@ -81,6 +81,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Builds every device table of every code in one blob (one cudaMalloc + one copy).
 int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
+    if (device < 0 || device >= kMaxDevices) return set_error(LDPC_ERR_BAD_ARGUMENT, "device ordinal out of range");
     CUDA_TRY(cudaSetDevice(device));
     std::unique_ptr<DeviceCtx> ctx(new DeviceCtx());
     ctx->device = device;
@@ -167,6 +168,28 @@ int ctx_for_device_locked(int device, DeviceCtx **out, std::mutex **mu_out) {
 
 }  // namespace
 
+WorkCounter::WorkCounter(DeviceCtx &ctx, cudaStream_t stream) : ctx_(ctx), stream_(stream) {
+    if (!ctx.counters) {
+        err_ = cudaMalloc(&ctx.counters, sizeof(unsigned long long) * DeviceCtx::kCounterStride * DeviceCtx::kCounterSlots);
+        if (err_ != cudaSuccess) return;
+    }
+    const int s = ctx.counter_next;
+    ctx.counter_next = (s + 1) % DeviceCtx::kCounterSlots;
+    if (ctx.counter_done[s]) {
+        err_ = cudaStreamWaitEvent(stream, ctx.counter_done[s], 0);      // the slot's previous user, whatever its stream
+    } else {
+        err_ = cudaEventCreateWithFlags(&ctx.counter_done[s], cudaEventDisableTiming);
+    }
+    if (err_ != cudaSuccess) return;
+    ptr_ = ctx.counters + (size_t)s * DeviceCtx::kCounterStride;
+    err_ = cudaMemsetAsync(ptr_, 0, sizeof(unsigned long long), stream);
+    slot_ = s;
+}
+
+WorkCounter::~WorkCounter() {
+    if (slot_ >= 0) cudaEventRecord(ctx_.counter_done[slot_], stream_);
+}
+
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 const char *last_error() { return t_last_error.c_str(); }
@@ -214,6 +237,10 @@ void runtime_shutdown() {
             if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
         }
         if (c->vscratch) cudaFree(c->vscratch);
+        if (c->vscratch_done) { cudaEventSynchronize(c->vscratch_done); cudaEventDestroy(c->vscratch_done); }
+        for (int i = 0; i < DeviceCtx::kCounterSlots; i++)
+            if (c->counter_done[i]) { cudaEventSynchronize(c->counter_done[i]); cudaEventDestroy(c->counter_done[i]); }
+        if (c->counters) cudaFree(c->counters);
         if (c->small_host) cudaFreeHost(c->small_host);
         if (c->retry_done) { cudaEventSynchronize(c->retry_done); cudaEventDestroy(c->retry_done); }
         if (c->retry_list) cudaFree(c->retry_list);

@@ -11,6 +11,9 @@
 
 namespace ldpc {
 
+// Device ordinals the per-kernel "already configured" tables are sized for; contexts for larger ordinals are refused.
+constexpr int kMaxDevices = 64;
+
 enum LlrType : int { kI8 = 0, kI16 = 1, kI32 = 2, kF32 = 3, kF64 = 4, kNumLlrTypes = 5 };
 
 inline size_t llr_size(int t) {
@@ -62,6 +65,15 @@ struct DeviceCtx {
     // scratch for decode paths whose message array does not fit in shared memory
     void *vscratch = nullptr;
     size_t vscratch_bytes = 0;
+    // event that orders the reuse of vscratch across streams (decode_ms_generic.cu)
+    cudaEvent_t vscratch_done = nullptr;
+    // work counters of the persistent kernels (class WorkCounter below): one slot per launch, reused round-robin;
+    // `counter_done[s]` is recorded behind the kernel that used slot s and awaited by the next user of the slot
+    static constexpr int kCounterSlots = 64;
+    static constexpr int kCounterStride = 16;   // 128 bytes apart: concurrent kernels never share a line
+    unsigned long long *counters = nullptr;
+    cudaEvent_t counter_done[kCounterSlots] = {};
+    int counter_next = 0;
     // list of undecided frames of the two-pass TC bit-flipping decoder (decode_bf_tc.cu); `retry_done` orders
     // its reuse across streams
     unsigned *retry_list = nullptr;
@@ -76,6 +88,27 @@ struct DeviceCtx {
     cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
     void *pipe_buf[kPipe] = {nullptr, nullptr, nullptr};
     size_t pipe_bytes[kPipe] = {0, 0, 0};
+};
+
+// A zeroed 8-byte frame-claim counter for ONE launch of a persistent kernel.  Construct it (under the context mutex,
+// like every launcher) before the launch and let it go out of scope after the launch: the destructor records the
+// slot's event on the stream, and the constructor makes the stream wait for the slot's previous user, so a slot is
+// never zeroed or claimed from while an earlier kernel -- on any stream -- still uses it.
+class WorkCounter {
+public:
+    WorkCounter(DeviceCtx &ctx, cudaStream_t stream);
+    ~WorkCounter();
+    WorkCounter(const WorkCounter &) = delete;
+    WorkCounter &operator=(const WorkCounter &) = delete;
+    cudaError_t error() const { return err_; }
+    unsigned long long *ptr() const { return ptr_; }
+
+private:
+    DeviceCtx &ctx_;
+    cudaStream_t stream_;
+    int slot_ = -1;
+    unsigned long long *ptr_ = nullptr;
+    cudaError_t err_ = cudaSuccess;
 };
 
 // Global launch counter (every kernel launch of this library increments it).

@@ -112,8 +112,5 @@ template <int RATE> TmParams make_params(const CodeInfo &c) {
     return prm;
 }
 
-// zeroed 8-byte work counter for one launch (ring per device; defined in decode_ms_tm.cu)
-cudaError_t next_counter(int device, cudaStream_t stream, unsigned long long **out);
-
 }  // namespace tm
 }  // namespace ldpc

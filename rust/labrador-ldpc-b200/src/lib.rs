@@ -193,6 +193,8 @@ impl LDPCCode {
         let batch = input.len() / (self.n() / 8);
         assert_eq!(input.len(), batch * self.n() / 8);
         assert_eq!(output.len(), batch * self.output_len());
+        assert_eq!(success.len(), batch);     // the C side writes `batch` entries into both
+        assert_eq!(iters.len(), batch);
         check(unsafe { ffi::labrador_ldpc_decode_bf_batch(self, input.as_ptr(), output.as_mut_ptr(), batch, maxiters,
                                                          success.as_mut_ptr(), iters.as_mut_ptr()) })
     }

@@ -295,3 +295,37 @@ def test_rust_binding_matches_header(ldpc):
     # enum discriminants are the reference's (src/codes/mod.rs:37-66)
     for i, name in enumerate(NAMES):
         assert re.search(r"\b%s = %d\b" % (name, i), src), name
+
+
+def test_batch_result_arrays_are_size_checked(ldpc):
+    """The C side writes `batch` entries into output / success / iters: the Python mirror must reject short
+    caller-supplied arrays before the call (no GPU needed: the check comes first)."""
+    c = ldpc.LDPCCode.TC128
+    llrs = np.zeros((3, 128), np.int8)
+    hard = np.zeros((3, 16), np.uint8)
+    ok3, it3, out3 = np.zeros(3, np.uint8), np.zeros(3, np.uint32), np.zeros((3, 16), np.uint8)
+    for kwargs in ({"success": np.zeros(2, np.uint8)}, {"iters": np.zeros(2, np.uint32)},
+                   {"output": np.zeros((2, 16), np.uint8)}, {"iters": np.zeros(3, np.uint16)}):
+        args = {"output": out3, "success": ok3, "iters": it3}
+        args.update(kwargs)
+        with pytest.raises(ValueError):
+            c.decode_ms_batch(llrs, 10, **args)
+        with pytest.raises(ValueError):
+            c.decode_bf_batch(hard, 10, **args)
+        with pytest.raises(ValueError):
+            c.decode_ms_hard_batch(hard, 10, **args)
+    with pytest.raises(ValueError):
+        c.hard_to_llrs_batch(hard, "i8", llrs=np.zeros((2, 128), np.int8))
+    with pytest.raises(ValueError):
+        c.llrs_to_hard_batch(llrs, output=np.zeros((2, 16), np.uint8))
+
+
+def test_rust_batch_functions_check_every_slice():
+    """Every safe `_batch` wrapper that hands success / iters to C asserts their lengths first."""
+    src = open(os.path.join(ROOT, "rust", "labrador-ldpc-b200", "src", "lib.rs")).read()
+    bodies = re.findall(r"pub fn (\w+_batch)[^{]*\{(.*?)\n    \}", src, flags=re.S)
+    assert len(bodies) >= 4
+    for name, body in bodies:
+        if "success.as_mut_ptr()" in body:
+            assert "assert_eq!(success.len(), batch)" in body, name
+            assert "assert_eq!(iters.len(), batch)" in body, name
