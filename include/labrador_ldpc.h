@@ -403,6 +403,12 @@ int labrador_ldpc_awgn_batch_async(enum labrador_ldpc_code code, int out_type, c
 int labrador_ldpc_count_errors_batch_async(enum labrador_ldpc_code code, const uint8_t *decoded, const uint8_t *data,
                                            uint32_t *bit_errors, size_t batch, void *cuda_stream);
 
+/* Copy-only control for the benchmark harness: moves the arrays of a host-pointer labrador_ldpc_decode_ms_*_batch
+ * call through the same chunked pipeline (H2D of llrs, D2H of output / success / iters_run) without launching a
+ * kernel; the result arrays receive unspecified bytes.  Host pointers only. */
+int labrador_ldpc_copy_control_batch(enum labrador_ldpc_code code, int llr_type, const void *llrs, uint8_t *output,
+                                     size_t batch, uint8_t *success, uint32_t *iters_run);
+
 /* Introspection used by the tests and the benchmark harness. */
 /* Number of kernels this library has launched since load (all devices). */
 unsigned long long labrador_ldpc_kernel_launch_count(void);

@@ -96,6 +96,7 @@ lib.labrador_ldpc_decode_ms_front_batch_async.argtypes = [_ci, _ci, _ci, _vp, _c
 lib.labrador_ldpc_quantise_i8_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz]
 lib.labrador_ldpc_quantise_i16_batch.argtypes = [_ci, _vp, _cf, _ci, _vp, _sz]
 lib.labrador_ldpc_quantise_batch_async.argtypes = [_ci, _ci, _vp, _cf, _ci, _vp, _sz, _vp]
+lib.labrador_ldpc_copy_control_batch.argtypes = [_ci, _ci, _vp, _vp, _sz, _vp, _vp]
 FRONT_NONE, FRONT_SOFT_F32, FRONT_HARD = 0, 1, 2
 _u64 = ctypes.c_uint64
 lib.labrador_ldpc_random_data_batch.argtypes = [_ci, _u64, _u64, _vp, _sz]
@@ -497,6 +498,16 @@ class LDPCCode(enum.IntEnum):
         else:
             _check(getattr(lib, "labrador_ldpc_llrs_to_hard_%s_batch" % ty)(int(self), _ptr(llrs), _ptr(output), batch))
         return output
+
+    def copy_control_batch(self, llrs, output, success, iters, ty=None):
+        """The host<->device transport of a host-buffer decode_ms_batch call without the kernel (bench.py's control)."""
+        ty = _llr_type(llrs, ty)
+        batch = self._batch_of(llrs, self.n() * np.dtype(_NP_OF[ty]).itemsize)
+        self._check_frames("output", output, batch, self.output_len())
+        self._check_frames("success", success, batch, 1)
+        self._check_frames("iters", iters, batch, 4)
+        _check(lib.labrador_ldpc_copy_control_batch(int(self), LLR_TYPES[ty], _ptr(llrs), _ptr(output), batch,
+                                                    _ptr(success), _ptr(iters)))
 
     def decode_ms_kernel_name(self, ty):
         return lib.labrador_ldpc_decode_ms_kernel_name(int(self), LLR_TYPES[ty]).decode()

@@ -421,6 +421,27 @@ int labrador_ldpc_llrs_to_hard_batch_async(enum labrador_ldpc_code code, int llr
     return l2h_impl(code, llr_type, llrs, output, batch, true, static_cast<cudaStream_t>(cuda_stream));
 }
 
+// Copy-only control of the host-pointer decode path: the same arrays go through the same chunked pipeline
+// (runtime.cu), but no kernel is launched.  What it measures is the host<->device transport alone.
+int labrador_ldpc_copy_control_batch(enum labrador_ldpc_code code, int llr_type, const void *llrs, uint8_t *output,
+                                     size_t batch, uint8_t *success, uint32_t *iters_run) {
+    const CodeInfo *c = info(code);
+    if (!c) return fail(LDPC_ERR_BAD_CODE, "code out of range");
+    if (llr_type < 0 || llr_type >= kNumLlrTypes) return fail(LDPC_ERR_BAD_ARGUMENT, "bad llr_type");
+    if (batch == 0) return LDPC_OK;
+    if (!llrs || !output) return fail(LDPC_ERR_NULL_POINTER, "llrs/output must not be NULL");
+    if (common_kind({llrs, output, success, iters_run}, nullptr) != 0)
+        return fail(LDPC_ERR_MIXED_POINTERS, "the copy control takes host pointers only");
+    std::vector<HostArray> arrays;
+    arrays.push_back({llrs, nullptr, (size_t)c->n * llr_size(llr_type)});
+    arrays.push_back({nullptr, output, c->output_len()});
+    if (success) arrays.push_back({nullptr, success, 1});
+    if (iters_run) arrays.push_back({nullptr, iters_run, 4});
+    return run_host_batch(arrays, batch, [](DeviceCtx &, const std::vector<void *> &, size_t, cudaStream_t) {
+        return cudaSuccess;
+    });
+}
+
 // ---- fused front ends (csrc/front.cuh) ----
 int labrador_ldpc_decode_ms_i8_soft_batch(enum labrador_ldpc_code code, const float *soft, float scale, int limit,
                                           uint8_t *output, size_t batch, size_t max_iters, uint8_t *success,

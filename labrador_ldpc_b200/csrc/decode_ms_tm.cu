@@ -699,9 +699,10 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
 
 }  // namespace
 
-// Variant selection.  Several arithmetic variants are compiled per code; the default per code is the one that
-// measured fastest on B200 (profiles/r01_tm_variants.md).  LABRADOR_LDPC_TM_ARITH=1|2|3|4|5 overrides (A/B runs);
-// 52 (TM5120 only) = ARITH 5 compiled for 2 resident CTAs per SM (128 registers, 15 spilled words).
+// Variant selection.  Several arithmetic variants are compiled per code; the default (632 = ARITH 6 with the in-thread
+// exit test, KNOBS 32) is the one that measured fastest on B200 for every code (profiles/r02_tm_variants.md).
+// LABRADOR_LDPC_TM_ARITH=1|2|3|4|5|6|7|532|616|632|716 overrides (A/B runs); 52 / 6322 (TM5120 only) = ARITH 5 / 632
+// compiled for 2 resident CTAs per SM (128 registers).
 template <int RATE, int M>
 cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const void *l, uint8_t *output,
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
@@ -738,6 +739,7 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 632) return launch_tm<RATE, M, 1, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 7) return launch_tm<RATE, M, 1, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
+        if (arith == 6322) return launch_tm<RATE, M, 1, 6, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 52) return launch_tm<RATE, M, 1, 5, 0, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     }
     if (arith == 4) return launch_tm<RATE, M, 1, 4, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -767,28 +769,28 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
     switch (code) {
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            if (ff) *err = launch_tm_front<1, 256, 1, 5, 0, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<1, 256>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 256, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 256>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<0, 512, 1, 2, 6, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<0, 512>(2, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 512, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 512>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<2, 512, 1, 5, 0, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<2, 512>(52, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 512, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<2, 512>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            if (ff) *err = launch_tm_front<1, 1024, 1, 5, 0, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<1, 1024>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 1024, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 1024>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            if (ff) *err = launch_tm_front<0, 2048, 2, 5, 0, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<0, 2048>(5, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 2048, 2, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 2048>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;

@@ -138,8 +138,6 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         d.enc_tc_lut = offs[ci].has_tc_lut ? reinterpret_cast<const uint32_t *>(base + offs[ci].tc_lut) : nullptr;
         d.enc_lut = offs[ci].has_ainv ? reinterpret_cast<const uint32_t *>(base + offs[ci].lut) : nullptr;
     }
-    for (int i = 0; i < DeviceCtx::kPipe; i++)
-        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
     out = std::move(ctx);
     return LDPC_OK;
 }
@@ -232,16 +230,20 @@ void runtime_shutdown() {
     cudaGetDevice(&prev);
     for (auto &c : r.ctxs) {
         cudaSetDevice(c->device);
-        for (int i = 0; i < DeviceCtx::kPipe; i++) {
-            if (c->pipe_stream[i]) { cudaStreamSynchronize(c->pipe_stream[i]); cudaStreamDestroy(c->pipe_stream[i]); }
-            if (c->pipe_buf[i]) cudaFree(c->pipe_buf[i]);
+        for (auto &lane : c->lanes) {
+            for (int i = 0; i < HostLane::kPipe; i++) {
+                if (lane->stream[i]) { cudaStreamSynchronize(lane->stream[i]); cudaStreamDestroy(lane->stream[i]); }
+                if (lane->buf[i]) cudaFree(lane->buf[i]);
+            }
+            if (lane->small_host) cudaFreeHost(lane->small_host);
         }
+        c->lanes.clear();
+        c->lanes_free.clear();
         if (c->vscratch) cudaFree(c->vscratch);
         if (c->vscratch_done) { cudaEventSynchronize(c->vscratch_done); cudaEventDestroy(c->vscratch_done); }
         for (int i = 0; i < DeviceCtx::kCounterSlots; i++)
             if (c->counter_done[i]) { cudaEventSynchronize(c->counter_done[i]); cudaEventDestroy(c->counter_done[i]); }
         if (c->counters) cudaFree(c->counters);
-        if (c->small_host) cudaFreeHost(c->small_host);
         if (c->retry_done) { cudaEventSynchronize(c->retry_done); cudaEventDestroy(c->retry_done); }
         if (c->retry_list) cudaFree(c->retry_list);
         if (c->table_blob) cudaFree(c->table_blob);
@@ -350,21 +352,64 @@ size_t chunk_bytes_target() {
     return v;
 }
 
+// A lane of the context's pool for the duration of one call (RAII; the pool is guarded by the context mutex).
+class LaneLease {
+public:
+    LaneLease(DeviceCtx &ctx, std::mutex &mu) : ctx_(ctx), mu_(mu) {
+        std::lock_guard<std::mutex> lock(mu_);
+        if (!ctx_.lanes_free.empty()) {
+            lane_ = ctx_.lanes_free.back();
+            ctx_.lanes_free.pop_back();
+            return;
+        }
+        std::unique_ptr<HostLane> lane(new HostLane());
+        for (int i = 0; i < HostLane::kPipe; i++) {
+            err_ = cudaStreamCreateWithFlags(&lane->stream[i], cudaStreamNonBlocking);
+            if (err_ != cudaSuccess) return;
+        }
+        lane_ = lane.get();
+        ctx_.lanes.push_back(std::move(lane));
+    }
+    ~LaneLease() {
+        if (!lane_) return;
+        std::lock_guard<std::mutex> lock(mu_);
+        ctx_.lanes_free.push_back(lane_);
+    }
+    HostLane *lane() const { return lane_; }
+    cudaError_t error() const { return err_; }
+
+private:
+    DeviceCtx &ctx_;
+    std::mutex &mu_;
+    HostLane *lane_ = nullptr;
+    cudaError_t err_ = cudaSuccess;
+};
+
+// Launchers touch per-context state (work counters, scratch): they run under the context mutex.  Copies and
+// synchronisation do not, so concurrent callers overlap everything but the launch call itself.
+cudaError_t locked_launch(DeviceCtx &ctx, std::mutex &mu, const BatchLaunchAt &launch, const std::vector<void *> &dptr,
+                          size_t frames, cudaStream_t st, size_t first) {
+    std::lock_guard<std::mutex> lock(mu);
+    return launch(ctx, dptr, frames, st, first);
+}
+
 int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<HostArray> &arrays, size_t first,
                             size_t count, const BatchLaunchAt &launch) {
-    std::lock_guard<std::mutex> lock(mu);
     CUDA_TRY(cudaSetDevice(ctx.device));
     size_t per_frame = 0;
     for (const HostArray &a : arrays) per_frame += align_up(a.bytes_per_frame, 16);
     if (per_frame == 0 || count == 0) return LDPC_OK;
+    LaneLease lease(ctx, mu);
+    if (lease.error() != cudaSuccess || !lease.lane()) return cuda_error(lease.error(), "stream create");
+    HostLane &lane = *lease.lane();
     // Small calls (the reference's single-codeword API is a batch of one): the arrays are packed into one pinned,
     // device-mapped block; the kernel reads its input and writes its results through that mapping, so the call is two
     // host memcpys, one launch and one stream synchronisation instead of a staged copy per array (profiles/r01_latency.md).
     static const bool small_path = [] { const char *e = getenv("LABRADOR_LDPC_SMALL_CALLS"); return !e || atoi(e) != 0; }();
-    if (small_path && per_frame * count + 256 * arrays.size() <= DeviceCtx::kSmallBytes) {
-        if (!ctx.small_host) {
-            CUDA_TRY(cudaHostAlloc(&ctx.small_host, DeviceCtx::kSmallBytes, cudaHostAllocMapped | cudaHostAllocPortable));
-            CUDA_TRY(cudaHostGetDevicePointer(&ctx.small_dev, ctx.small_host, 0));
+    if (small_path && per_frame * count + 256 * arrays.size() <= HostLane::kSmallBytes) {
+        if (!lane.small_host) {
+            CUDA_TRY(cudaHostAlloc(&lane.small_host, HostLane::kSmallBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+            CUDA_TRY(cudaHostGetDevicePointer(&lane.small_dev, lane.small_host, 0));
         }
         std::vector<void *> dptr(arrays.size());
         std::vector<size_t> off(arrays.size());
@@ -372,21 +417,21 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
         for (size_t i = 0; i < arrays.size(); i++) {
             off[i] = total;
             total += align_up(arrays[i].bytes_per_frame * count, 256);
-            dptr[i] = static_cast<unsigned char *>(ctx.small_dev) + off[i];
+            dptr[i] = static_cast<unsigned char *>(lane.small_dev) + off[i];
             if (arrays[i].host_in)
-                memcpy(static_cast<unsigned char *>(ctx.small_host) + off[i],
+                memcpy(static_cast<unsigned char *>(lane.small_host) + off[i],
                        static_cast<const unsigned char *>(arrays[i].host_in) + first * arrays[i].bytes_per_frame,
                        arrays[i].bytes_per_frame * count);
         }
-        cudaStream_t st = ctx.pipe_stream[0];
-        cudaError_t e = launch(ctx, dptr, count, st, first);
+        cudaStream_t st = lane.stream[0];
+        cudaError_t e = locked_launch(ctx, mu, launch, dptr, count, st, first);
         if (e != cudaSuccess) return cuda_error(e, "kernel launch");
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return cuda_error(e, "stream synchronize");
         for (size_t i = 0; i < arrays.size(); i++)
             if (arrays[i].host_out)
                 memcpy(static_cast<unsigned char *>(arrays[i].host_out) + first * arrays[i].bytes_per_frame,
-                       static_cast<unsigned char *>(ctx.small_host) + off[i], arrays[i].bytes_per_frame * count);
+                       static_cast<unsigned char *>(lane.small_host) + off[i], arrays[i].bytes_per_frame * count);
         return LDPC_OK;
     }
     size_t chunk = chunk_bytes_target() / per_frame;
@@ -401,20 +446,20 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
         total += align_up(arrays[i].bytes_per_frame * chunk, 256);
     }
     const size_t n_chunks = (count + chunk - 1) / chunk;
-    const int slots = (int)(n_chunks < (size_t)DeviceCtx::kPipe ? n_chunks : (size_t)DeviceCtx::kPipe);
+    const int slots = (int)(n_chunks < (size_t)HostLane::kPipe ? n_chunks : (size_t)HostLane::kPipe);
     for (int s = 0; s < slots; s++) {
-        if (ctx.pipe_bytes[s] < total) {
-            if (ctx.pipe_buf[s]) { CUDA_TRY(cudaStreamSynchronize(ctx.pipe_stream[s])); CUDA_TRY(cudaFree(ctx.pipe_buf[s])); }
-            ctx.pipe_buf[s] = nullptr; ctx.pipe_bytes[s] = 0;
-            CUDA_TRY(cudaMalloc(&ctx.pipe_buf[s], total));
-            ctx.pipe_bytes[s] = total;
+        if (lane.bytes[s] < total) {
+            if (lane.buf[s]) { CUDA_TRY(cudaStreamSynchronize(lane.stream[s])); CUDA_TRY(cudaFree(lane.buf[s])); }
+            lane.buf[s] = nullptr; lane.bytes[s] = 0;
+            CUDA_TRY(cudaMalloc(&lane.buf[s], total));
+            lane.bytes[s] = total;
         }
     }
     int rc = LDPC_OK;
     for (size_t c = 0; c < n_chunks && rc == LDPC_OK; c++) {
-        const int s = (int)(c % DeviceCtx::kPipe);
-        cudaStream_t st = ctx.pipe_stream[s];
-        unsigned char *base = static_cast<unsigned char *>(ctx.pipe_buf[s]);
+        const int s = (int)(c % HostLane::kPipe);
+        cudaStream_t st = lane.stream[s];
+        unsigned char *base = static_cast<unsigned char *>(lane.buf[s]);
         const size_t f0 = first + c * chunk;
         const size_t nf = (c + 1 == n_chunks) ? (count - c * chunk) : chunk;
         std::vector<void *> dptr(arrays.size());
@@ -428,7 +473,7 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
             }
         }
         if (rc != LDPC_OK) break;
-        cudaError_t e = launch(ctx, dptr, nf, st, f0);
+        cudaError_t e = locked_launch(ctx, mu, launch, dptr, nf, st, f0);
         if (e != cudaSuccess) { rc = cuda_error(e, "kernel launch"); break; }
         for (size_t i = 0; i < arrays.size(); i++) {
             const HostArray &a = arrays[i];
@@ -440,7 +485,7 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
         }
     }
     for (int s = 0; s < slots; s++) {
-        cudaError_t e = cudaStreamSynchronize(ctx.pipe_stream[s]);
+        cudaError_t e = cudaStreamSynchronize(lane.stream[s]);
         if (e != cudaSuccess && rc == LDPC_OK) rc = cuda_error(e, "stream synchronize");
     }
     return rc;

@@ -5,7 +5,9 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <vector>
 
 #include "code_tables.h"
 
@@ -56,6 +58,21 @@ struct DeviceCode {
     const uint32_t *enc_lut;   // TM codes: the same as a nibble lookup table (code_tables.h: tm_encoder_lut), else null
 };
 
+// Everything one host thread needs to push a host-pointer batch through a device: its own streams, device chunk
+// buffers and pinned staging block.  Lanes live in a pool of the device context (DeviceCtx::lanes), so concurrent
+// callers -- the reference's usage is one decoder per host thread, perftest/src/main.rs:39-45 -- never share a
+// stream or a buffer and only meet at the context mutex for the few microseconds of a kernel launch.
+struct HostLane {
+    static constexpr int kPipe = 3;
+    static constexpr size_t kSmallBytes = 256 << 10;
+    cudaStream_t stream[kPipe] = {nullptr, nullptr, nullptr};
+    void *buf[kPipe] = {nullptr, nullptr, nullptr};
+    size_t bytes[kPipe] = {0, 0, 0};
+    // small calls (the single-codeword reference API): one pinned, device-mapped staging block
+    void *small_host = nullptr;   // host address
+    void *small_dev = nullptr;    // the same block as the device sees it
+};
+
 struct DeviceCtx {
     int device = -1;
     int sm_count = 0;
@@ -79,15 +96,9 @@ struct DeviceCtx {
     unsigned *retry_list = nullptr;
     size_t retry_list_bytes = 0;
     cudaEvent_t retry_done = nullptr;
-    // small host-pointer calls (the single-codeword reference API): one pinned, device-mapped staging block
-    void *small_host = nullptr;   // host address
-    void *small_dev = nullptr;    // the same block as the device sees it
-    static constexpr size_t kSmallBytes = 256 << 10;
-    // host-pointer pipeline
-    static constexpr int kPipe = 3;
-    cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr};
-    void *pipe_buf[kPipe] = {nullptr, nullptr, nullptr};
-    size_t pipe_bytes[kPipe] = {0, 0, 0};
+    // host-pointer pipeline: pool of per-caller lanes (guarded by the context mutex)
+    std::vector<std::unique_ptr<HostLane>> lanes;
+    std::vector<HostLane *> lanes_free;
 };
 
 // A zeroed 8-byte frame-claim counter for ONE launch of a persistent kernel.  Construct it (under the context mutex,

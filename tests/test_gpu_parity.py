@@ -324,7 +324,7 @@ def test_tc_packed_pair_kernel_streams(ldpc, oracle, code):
     assert len(set(want[2].tolist())) > 5, "needs a spread of iteration counts"
 
 
-@pytest.mark.parametrize("code", [0, 2, 3, 5, 8])
+@pytest.mark.parametrize("code", CODES)
 @pytest.mark.parametrize("ty", ["i16", "i32"])
 def test_decode_ms_wide_int_awgn_exact(ldpc, oracle, code, ty):
     c = ldpc.LDPCCode(code)
@@ -593,9 +593,10 @@ def test_full_size_properties_tm8192(ldpc, oracle):
     assert torch.equal(reenc[okb], out[okb][:, : c.n() // 8])
     assert int(iters[okb].max()) < 100 and bool((iters[~okb] == 100).all())
     # exact parity with the oracle on a prefix of the very same LLR bytes
-    sample = llrs[:96].cpu().numpy()
-    want = oracle.decode_ms_batch(code, sample, 100, nthreads=8)
-    assert_exact((out[:96].cpu().numpy(), ok[:96].cpu().numpy(), iters[:96].cpu().numpy()), want, "prefix sample")
+    ns = 2048
+    sample = llrs[:ns].cpu().numpy()
+    want = oracle.decode_ms_batch(code, sample, 100, nthreads=16)
+    assert_exact((out[:ns].cpu().numpy(), ok[:ns].cpu().numpy(), iters[:ns].cpu().numpy()), want, "prefix sample")
 
 
 def test_shutdown_and_reinitialise(ldpc, oracle):
@@ -741,3 +742,57 @@ print("OK")
 ''' % (root, root, root)
     out = subprocess.check_output([sys.executable, "-c", script], text=True)
     assert "OK" in out
+
+
+def test_cuda_tensor_calls_follow_the_current_stream(ldpc, oracle):
+    """Single-codeword calls on CUDA tensors are ordered on torch's CURRENT stream (side streams are non-blocking
+    with respect to the legacy default stream): input produced on a side stream right before the call must be seen."""
+    import torch
+    code = 5
+    c = ldpc.LDPCCode(code)
+    _, cw, llrs = make_frames(oracle, code, 1, 3.0, seed=77, ty="i8")
+    want_ok, want_it, want_out = oracle.decode_ms(code, llrs[0], 50)
+    src = torch.from_numpy(llrs[0]).cuda()
+    data = torch.from_numpy(cw[0, : c.k() // 8].copy()).cuda()
+    busy = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(8):
+            busy.add_(1)                       # a few ms of work ahead of the producer on the side stream
+        llr_d = torch.zeros(c.n(), dtype=torch.int8, device="cuda")
+        llr_d.copy_(src)                       # the producer
+        out_d = torch.zeros(c.output_len(), dtype=torch.uint8, device="cuda")
+        ok, it = c.decode_ms(llr_d, out_d, maxiters=50)
+        cw_d = torch.zeros(c.n() // 8, dtype=torch.uint8, device="cuda")
+        dat_d = torch.zeros(c.k() // 8, dtype=torch.uint8, device="cuda")
+        dat_d.copy_(data)
+        c.copy_encode(dat_d, cw_d)
+        h_d = torch.zeros(c.n() // 8, dtype=torch.uint8, device="cuda")
+        c.llrs_to_hard(llr_d, h_d)
+    side.synchronize()
+    assert (ok, it) == (want_ok, want_it)
+    assert np.array_equal(out_d.cpu().numpy(), want_out)
+    assert np.array_equal(cw_d.cpu().numpy(), cw[0])
+    assert np.array_equal(h_d.cpu().numpy(), oracle.llrs_to_hard(code, llrs[0]))
+
+
+def test_many_async_launches_on_several_streams(ldpc, oracle):
+    """More stream-ordered launches in flight than the context has work-counter slots (64), spread over four
+    streams and three kernel families: every launch must still claim exactly its own frames."""
+    import torch
+    jobs = []
+    for code, eb, batch in ((4, 2.6, 40), (0, 3.0, 300), (5, 1.8, 24)):
+        _, _, llrs = make_frames(oracle, code, batch, eb, seed=900 + code, ty="i8")
+        jobs.append((ldpc.LDPCCode(code), torch.from_numpy(llrs).cuda(), oracle.decode_ms_batch(code, llrs, 30, nthreads=8)))
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    results = []
+    torch.cuda.synchronize()
+    for i in range(200):
+        c, l, want = jobs[i % len(jobs)]
+        st = streams[i % len(streams)]
+        with torch.cuda.stream(st):
+            results.append((c.decode_ms_batch(l, 30, stream=st.cuda_stream), want, c.name))
+    torch.cuda.synchronize()
+    for got, want, name in results:
+        assert_exact([g.cpu().numpy() for g in got], want, "async " + name)

@@ -41,6 +41,15 @@ if __name__ == "__main__":
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     itf = it.float()
+    meta = os.environ.get("QUICK_TIME_META")
+    if meta:      # facts about the (identical) launches of this run, for tools/ncu_export.py
+        import json
+        edges = {0: 512, 1: 1024, 2: 2048, 3: 4992, 4: 5888, 5: 7680, 6: 19968, 7: 23552, 8: 30720}[code]
+        upd = torch.where(ok.bool(), it.double() + 1.0, it.double()).sum().item() * 2.0 * edges
+        json.dump({"code": c.name, "llr_type": ty, "frames": batch, "ebn0_db": ebn0, "max_iters": 100,
+                   "mean_iters": itf.mean().item(), "success": ok.float().mean().item(), "edge_updates": upd,
+                   "variant": os.environ.get("LABRADOR_LDPC_TM_ARITH", "default"),
+                   "command": "tools/quick_time.py " + " ".join(sys.argv[1:])}, open(meta, "w"))
     print("%s %s batch %d ebn0 %.1f kernel %s: %.3f ms  %.0f cw/s  %.2f Gbit/s info  succ %.4f iters mean %.2f max %d" % (
         c.name, ty, batch, ebn0, c.decode_ms_kernel_name(ty), ms, batch / ms * 1e3, batch * c.k() / ms / 1e6,
         ok.float().mean().item(), itf.mean().item(), int(it.max())))
