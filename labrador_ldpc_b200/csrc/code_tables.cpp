@@ -29,6 +29,12 @@ const Raw kRaw[kNumCodes] = {
     {"TM5120", 5120, 4096, 512, 512, 128, 19968, ccsds_proto_tm_r45, ccsds_phi_m512, ccsds_gen_tm5120},
     {"TM6144", 6144, 4096, 1024, 1024, 256, 23552, ccsds_proto_tm_r23, ccsds_phi_m1024, ccsds_gen_tm6144},
     {"TM8192", 8192, 4096, 2048, 2048, 512, 30720, ccsds_proto_tm_r12, ccsds_phi_m2048, ccsds_gen_tm8192},
+    // k = 16384 (CCSDS 131.0-B: M = 2048 / 4096 / 8192 for rates 4/5, 2/3, 1/2; compact_parity_checks.rs:84-96).  The
+    // reference ships their prototypes and phi tables but no generators (src/lib.rs:81-83): p = M, b = M/4 and
+    // edges = blocks x M follow the pattern of the six smaller TM codes.
+    {"TM20480", 20480, 16384, 2048, 2048, 512, 39 * 2048, ccsds_proto_tm_r45, ccsds_phi_m2048, nullptr},
+    {"TM24576", 24576, 16384, 4096, 4096, 1024, 23 * 4096, ccsds_proto_tm_r23, ccsds_phi_m4096, nullptr},
+    {"TM32768", 32768, 16384, 8192, 8192, 2048, 15 * 8192, ccsds_proto_tm_r12, ccsds_phi_m8192, nullptr},
 };
 
 CodeInfo g_info[kNumCodes];
@@ -125,18 +131,64 @@ uint32_t edge_crc(const CodeInfo &c) {
     return crc;
 }
 
-void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::vector<uint32_t> &chk_tab) {
+void build_ell_tables(const CodeInfo &c, std::vector<uint64_t> &var_tab, std::vector<uint64_t> &chk_tab) {
     std::vector<uint32_t> chk, var;
     expand_edges(c, chk, var);
-    var_tab.assign((size_t)c.max_var_degree * c.vars, kNoEdge);
-    chk_tab.assign((size_t)c.max_check_degree * c.checks, kNoEdge);
+    var_tab.assign((size_t)c.max_var_degree * c.vars, kNoEdge64);
+    chk_tab.assign((size_t)c.max_check_degree * c.checks, kNoEdge64);
     std::vector<int> vfill(c.vars, 0), cfill(c.checks, 0);
     for (uint32_t idx = 0; idx < chk.size(); idx++) {
         const uint32_t a = var[idx], ch = chk[idx];
-        var_tab[(size_t)vfill[a]++ * c.vars + a] = idx | (ch << 16);
-        chk_tab[(size_t)cfill[ch]++ * c.checks + ch] = idx | (a << 16);
+        var_tab[(size_t)vfill[a]++ * c.vars + a] = (uint64_t)idx | ((uint64_t)ch << 32);
+        chk_tab[(size_t)cfill[ch]++ * c.checks + ch] = (uint64_t)idx | ((uint64_t)a << 32);
     }
 }
+
+namespace {
+
+// Arithmetic in R = GF(2)[x] / (x^Q - 1), Q a power of two >= 32: a Q x Q circulant with first column a is the
+// polynomial sum a_z x^z, products of circulants are products in R.  Since x^Q - 1 = (x + 1)^Q, R is a local ring: a is
+// a unit iff its weight is odd, and then a^Q = a(x^Q) = a(1) = 1, so a^-1 = a^(Q-1) = a * a^2 * a^4 * ... * a^(Q/2).
+struct Poly {
+    int q;
+    std::vector<uint64_t> w;
+    explicit Poly(int q_) : q(q_), w(q_ >= 64 ? q_ / 64 : 1, 0) {}
+    bool bit(int z) const { return (w[z >> 6] >> (z & 63)) & 1; }
+    void flip(int z) { w[z >> 6] ^= 1ull << (z & 63); }
+    bool zero() const { for (uint64_t x : w) if (x) return false; return true; }
+    bool unit() const { int p = 0; for (uint64_t x : w) p ^= __builtin_parityll(x); return p != 0; }
+    void add(const Poly &o) { for (size_t i = 0; i < w.size(); i++) w[i] ^= o.w[i]; }
+    // this += o * x^z
+    void add_rot(const Poly &o, int z) {
+        if (q < 64) {
+            const uint64_t m = (1ull << q) - 1, v = o.w[0];
+            w[0] ^= z ? (((v << z) | (v >> (q - z))) & m) : v;
+            return;
+        }
+        const int W = (int)w.size(), ws = z >> 6, bs = z & 63;
+        for (int i = 0; i < W; i++) {
+            const uint64_t lo = o.w[(i - ws + W) % W], hi = o.w[(i - ws - 1 + 2 * W) % W];
+            w[i] ^= bs ? ((lo << bs) | (hi >> (64 - bs))) : lo;
+        }
+    }
+    Poly mul(const Poly &o) const {
+        Poly r(q);
+        for (int z = 0; z < q; z++) if (bit(z)) r.add_rot(o, z);
+        return r;
+    }
+    Poly square() const {             // a(x)^2 = a(x^2): x^z -> x^(2z mod Q); z and z + Q/2 collide and cancel
+        Poly r(q);
+        for (int z = 0; z < q; z++) if (bit(z)) r.flip((2 * z) % q);
+        return r;
+    }
+    Poly inverse() const {            // requires unit()
+        Poly r(*this), s(*this);
+        for (int e = 2; e < q; e <<= 1) { s = s.square(); r = r.mul(s); }
+        return r;
+    }
+};
+
+}  // namespace
 
 bool tm_encoder_table(int code, std::vector<uint32_t> &out) {
     out.clear();
@@ -162,41 +214,44 @@ bool tm_encoder_table(int code, std::vector<uint32_t> &out) {
         } else if (b.row == 0) return false;            // row 0 has no data terms
     }
     if (ident_ok != 7 || s_blocks.empty() || g_blocks.empty()) return false;
-    // A = I + S G as bit rows, augmented with the four right-hand sides e_{qj Q}
-    const int RW = M / 64 + 1;
-    std::vector<uint64_t> a((size_t)M * RW, 0);
-    auto flip = [&](int r, int col) { a[(size_t)r * RW + (col >> 6)] ^= 1ull << (col & 63); };
-    for (int i = 0; i < M; i++) {
-        flip(i, i);
-        for (const Block *s : s_blocks)
-            for (const Block *g : g_blocks) flip(i, block_pi(c, *g, block_pi(c, *s, i)));
+    // Every pi_k is a 4 x 4 array of circulants with one monomial per block row: check quarter j, offset i' goes to variable
+    // quarter (theta + j) mod 4, offset (phi_j + i') mod Q, i.e. block (j, (theta + j) mod 4) has the first column
+    // x^(-phi_j).  A = I + (sum of the S blocks)(sum of the G blocks) is inverted by Gauss-Jordan over the ring
+    // (pivots must be units; 4 x 4, so even M = 8192 takes milliseconds where the bit matrix would take seconds).
+    auto block_matrix = [&](const std::vector<const Block *> &blocks) {
+        std::vector<Poly> m(16, Poly(Q));
+        for (const Block *b : blocks)
+            for (int j = 0; j < 4; j++) m[(size_t)j * 4 + (b->theta + j) % 4].flip((Q - b->phi[j] % Q) % Q);
+        return m;
+    };
+    const std::vector<Poly> sm = block_matrix(s_blocks), gm = block_matrix(g_blocks);
+    std::vector<Poly> a(32, Poly(Q));                     // [row][col 0..3 = A, 4..7 = identity]
+    for (int i = 0; i < 4; i++) {
+        a[(size_t)i * 8 + i].flip(0);
+        a[(size_t)i * 8 + 4 + i].flip(0);
+        for (int j = 0; j < 4; j++)
+            for (int k = 0; k < 4; k++)
+                if (!sm[(size_t)i * 4 + k].zero() && !gm[(size_t)k * 4 + j].zero())
+                    a[(size_t)i * 8 + j].add(sm[(size_t)i * 4 + k].mul(gm[(size_t)k * 4 + j]));
     }
-    for (int qj = 0; qj < 4; qj++) flip(qj * Q, M + qj);
-    // Gauss-Jordan over GF(2)
-    for (int col = 0; col < M; col++) {
+    for (int col = 0; col < 4; col++) {
         int piv = -1;
-        for (int r = col; r < M; r++)
-            if ((a[(size_t)r * RW + (col >> 6)] >> (col & 63)) & 1) { piv = r; break; }
+        for (int r = col; r < 4; r++) if (a[(size_t)r * 8 + col].unit()) { piv = r; break; }
         if (piv < 0) return false;
-        if (piv != col)
-            for (int w = 0; w < RW; w++) std::swap(a[(size_t)piv * RW + w], a[(size_t)col * RW + w]);
-        const uint64_t *prow = &a[(size_t)col * RW];
-        const int w0 = col >> 6;
-        for (int r = 0; r < M; r++) {
-            if (r == col) continue;
-            uint64_t *row = &a[(size_t)r * RW];
-            if ((row[w0] >> (col & 63)) & 1)
-                for (int w = w0; w < RW; w++) row[w] ^= prow[w];
+        if (piv != col) for (int j = 0; j < 8; j++) std::swap(a[(size_t)piv * 8 + j], a[(size_t)col * 8 + j]);
+        const Poly inv = a[(size_t)col * 8 + col].inverse();
+        for (int j = 0; j < 8; j++) a[(size_t)col * 8 + j] = inv.mul(a[(size_t)col * 8 + j]);
+        for (int r = 0; r < 4; r++) {
+            if (r == col || a[(size_t)r * 8 + col].zero()) continue;
+            const Poly f = a[(size_t)r * 8 + col];
+            for (int j = 0; j < 8; j++) a[(size_t)r * 8 + j].add(f.mul(a[(size_t)col * 8 + j]));
         }
     }
     out.assign((size_t)16 * QW, 0);
     for (int qi = 0; qi < 4; qi++)
         for (int qj = 0; qj < 4; qj++)
-            for (int z = 0; z < Q; z++) {
-                const int bit = M + qj;
-                if ((a[(size_t)(qi * Q + z) * RW + (bit >> 6)] >> (bit & 63)) & 1)
-                    out[(size_t)(qi * 4 + qj) * QW + (z >> 5)] |= 1u << (z & 31);
-            }
+            for (int z = 0; z < Q; z++)
+                if (a[(size_t)qi * 8 + 4 + qj].bit(z)) out[(size_t)(qi * 4 + qj) * QW + (z >> 5)] |= 1u << (z & 31);
     return true;
 }
 

@@ -1,4 +1,5 @@
-// Host-side description of the nine CCSDS codes and the one-time expansion of
+// Host-side description of the CCSDS codes -- the reference's nine plus the three k = 16384 TM codes whose parity-check
+// constants the reference carries without supporting them (src/lib.rs:81-83) -- and the one-time expansion of
 // the compact parity-check prototypes into block descriptors and edge tables.
 //
 // Replaces (as data, built once per process instead of re-derived per edge):
@@ -12,7 +13,8 @@
 
 namespace ldpc {
 
-constexpr int kNumCodes = 9;
+constexpr int kNumCodes = 12;       // 0..8: enum LDPCCode of the reference (src/codes/mod.rs:37-66); 9..11: TM20480 / TM24576 / TM32768
+constexpr int kNumRefCodes = 9;
 constexpr int kMaxBlocks = 40;     // r4/5 prototype has 39 non-zero blocks
 constexpr uint32_t kNoEdge = 0xFFFFFFFFu;
 
@@ -38,7 +40,7 @@ struct CodeInfo {
     int checks;              // n + p - k
     int vars;                // n + p
     int rows, cols;          // active prototype rows / columns
-    const uint64_t *gen;     // compact generator, (k/b) x ((n-k)/64) words, MSB = parity bit 0
+    const uint64_t *gen;     // compact generator, (k/b) x ((n-k)/64) words, MSB = parity bit 0; nullptr for the k = 16384 codes
     int n_blocks;
     Block blocks[kMaxBlocks];
     int max_var_degree, max_check_degree;
@@ -59,11 +61,12 @@ void expand_edges(const CodeInfo &c, std::vector<uint32_t> &check, std::vector<u
 // CRC-32 over the ordered edge list as in reference src/codes/mod.rs:508-535.
 uint32_t edge_crc(const CodeInfo &c);
 
-// ELL tables for the generic kernels.
-//   var_tab[j*vars + a]   = idx | check << 16   j-th edge of variable a in ascending idx order
-//   chk_tab[j*checks + c] = idx | var   << 16   j-th edge of check c in ascending idx order
-// Missing entries are kNoEdge.
-void build_ell_tables(const CodeInfo &c, std::vector<uint32_t> &var_tab, std::vector<uint32_t> &chk_tab);
+// ELL tables for the generic kernels (64-bit entries: the k = 16384 codes have more than 2^16 edges).
+//   var_tab[j*vars + a]   = idx | check << 32   j-th edge of variable a in ascending idx order
+//   chk_tab[j*checks + c] = idx | var   << 32   j-th edge of check c in ascending idx order
+// Missing entries are kNoEdge64.
+constexpr uint64_t kNoEdge64 = ~0ull;
+void build_ell_tables(const CodeInfo &c, std::vector<uint64_t> &var_tab, std::vector<uint64_t> &chk_tab);
 
 // Table of the parity-check-based TM encoder (encode_tm.cu).  In every TM prototype the three parity block
 // columns (CA, CB transmitted, CC punctured) sit in H as

@@ -779,8 +779,8 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<2, 512, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<2, 512>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 512, 1, 6, 32, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<2, 512>(6322, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
