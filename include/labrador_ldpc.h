@@ -38,8 +38,16 @@ enum labrador_ldpc_code {
     LABRADOR_LDPC_CODE_TM5120 = 6, /* n=5120 k=4096 r=4/5 */
     LABRADOR_LDPC_CODE_TM6144 = 7, /* n=6144 k=4096 r=2/3 */
     LABRADOR_LDPC_CODE_TM8192 = 8, /* n=8192 k=4096 r=1/2 */
+    /* Extension (not in the reference's enum): the k = 16384 codes of CCSDS 131.0-B.  The reference carries their
+     * parity-check constants (src/codes/compact_parity_checks.rs:84-96, PHI_J_K_M4096 / M8192, selected at
+     * src/codes/mod.rs:473-476) but leaves the codes out for want of generator matrices (src/lib.rs:81-83).  Here they
+     * are decoded like every TM code and encoded through the sparse parity-check matrix, which needs no generator. */
+    LABRADOR_LDPC_CODE_TM20480 = 9,  /* n=20480 k=16384 r=4/5 */
+    LABRADOR_LDPC_CODE_TM24576 = 10, /* n=24576 k=16384 r=2/3 */
+    LABRADOR_LDPC_CODE_TM32768 = 11, /* n=32768 k=16384 r=1/2 */
 };
-#define LABRADOR_LDPC_NUM_CODES 9
+#define LABRADOR_LDPC_NUM_CODES 12
+#define LABRADOR_LDPC_NUM_REFERENCE_CODES 9
 
 /* ---------------------------------------------------------------------------
  * Compile-time sizes.  Replaces capi/include/labrador_ldpc.h:42-115.
@@ -97,6 +105,18 @@ enum labrador_ldpc_code {
 #define LABRADOR_LDPC_K_TM8192 (4096)
 #define LABRADOR_LDPC_P_TM8192 (2048)
 #define LABRADOR_LDPC_E_TM8192 (30720)
+#define LABRADOR_LDPC_N_TM20480 (20480)
+#define LABRADOR_LDPC_K_TM20480 (16384)
+#define LABRADOR_LDPC_P_TM20480 (2048)
+#define LABRADOR_LDPC_E_TM20480 (79872)
+#define LABRADOR_LDPC_N_TM24576 (24576)
+#define LABRADOR_LDPC_K_TM24576 (16384)
+#define LABRADOR_LDPC_P_TM24576 (4096)
+#define LABRADOR_LDPC_E_TM24576 (94208)
+#define LABRADOR_LDPC_N_TM32768 (32768)
+#define LABRADOR_LDPC_K_TM32768 (16384)
+#define LABRADOR_LDPC_P_TM32768 (8192)
+#define LABRADOR_LDPC_E_TM32768 (122880)
 
 #define LABRADOR_LDPC_N_(CODE) LABRADOR_LDPC_N_##CODE
 #define LABRADOR_LDPC_N(CODE) LABRADOR_LDPC_N_(CODE)
@@ -126,6 +146,9 @@ enum labrador_ldpc_code {
 #define LABRADOR_LDPC_BF_WORKING_LEN_TM6144 LABRADOR_LDPC_BF_WORKING_LEN(TM6144)
 #define LABRADOR_LDPC_BF_WORKING_LEN_TM6140 LABRADOR_LDPC_BF_WORKING_LEN(TM6144)
 #define LABRADOR_LDPC_BF_WORKING_LEN_TM8192 LABRADOR_LDPC_BF_WORKING_LEN(TM8192)
+#define LABRADOR_LDPC_BF_WORKING_LEN_TM20480 LABRADOR_LDPC_BF_WORKING_LEN(TM20480)
+#define LABRADOR_LDPC_BF_WORKING_LEN_TM24576 LABRADOR_LDPC_BF_WORKING_LEN(TM24576)
+#define LABRADOR_LDPC_BF_WORKING_LEN_TM32768 LABRADOR_LDPC_BF_WORKING_LEN(TM32768)
 #define LABRADOR_LDPC_MS_WORKING_LEN_TC128 LABRADOR_LDPC_MS_WORKING_LEN(TC128)
 #define LABRADOR_LDPC_MS_WORKING_LEN_TC256 LABRADOR_LDPC_MS_WORKING_LEN(TC256)
 #define LABRADOR_LDPC_MS_WORKING_LEN_TC512 LABRADOR_LDPC_MS_WORKING_LEN(TC512)
@@ -136,6 +159,9 @@ enum labrador_ldpc_code {
 #define LABRADOR_LDPC_MS_WORKING_LEN_TM6144 LABRADOR_LDPC_MS_WORKING_LEN(TM6144)
 #define LABRADOR_LDPC_MS_WORKING_LEN_TM6140 LABRADOR_LDPC_MS_WORKING_LEN(TM6144)
 #define LABRADOR_LDPC_MS_WORKING_LEN_TM8192 LABRADOR_LDPC_MS_WORKING_LEN(TM8192)
+#define LABRADOR_LDPC_MS_WORKING_LEN_TM20480 LABRADOR_LDPC_MS_WORKING_LEN(TM20480)
+#define LABRADOR_LDPC_MS_WORKING_LEN_TM24576 LABRADOR_LDPC_MS_WORKING_LEN(TM24576)
+#define LABRADOR_LDPC_MS_WORKING_LEN_TM32768 LABRADOR_LDPC_MS_WORKING_LEN(TM32768)
 #define LABRADOR_LDPC_MS_WORKING_U8_LEN_TC128 LABRADOR_LDPC_MS_WORKING_U8_LEN(TC128)
 #define LABRADOR_LDPC_MS_WORKING_U8_LEN_TC256 LABRADOR_LDPC_MS_WORKING_U8_LEN(TC256)
 #define LABRADOR_LDPC_MS_WORKING_U8_LEN_TC512 LABRADOR_LDPC_MS_WORKING_U8_LEN(TC512)
@@ -146,6 +172,9 @@ enum labrador_ldpc_code {
 #define LABRADOR_LDPC_MS_WORKING_U8_LEN_TM6144 LABRADOR_LDPC_MS_WORKING_U8_LEN(TM6144)
 #define LABRADOR_LDPC_MS_WORKING_U8_LEN_TM6140 LABRADOR_LDPC_MS_WORKING_U8_LEN(TM6144)
 #define LABRADOR_LDPC_MS_WORKING_U8_LEN_TM8192 LABRADOR_LDPC_MS_WORKING_U8_LEN(TM8192)
+#define LABRADOR_LDPC_MS_WORKING_U8_LEN_TM20480 LABRADOR_LDPC_MS_WORKING_U8_LEN(TM20480)
+#define LABRADOR_LDPC_MS_WORKING_U8_LEN_TM24576 LABRADOR_LDPC_MS_WORKING_U8_LEN(TM24576)
+#define LABRADOR_LDPC_MS_WORKING_U8_LEN_TM32768 LABRADOR_LDPC_MS_WORKING_U8_LEN(TM32768)
 #define LABRADOR_LDPC_OUTPUT_LEN_TC128 LABRADOR_LDPC_OUTPUT_LEN(TC128)
 #define LABRADOR_LDPC_OUTPUT_LEN_TC256 LABRADOR_LDPC_OUTPUT_LEN(TC256)
 #define LABRADOR_LDPC_OUTPUT_LEN_TC512 LABRADOR_LDPC_OUTPUT_LEN(TC512)
@@ -156,6 +185,9 @@ enum labrador_ldpc_code {
 #define LABRADOR_LDPC_OUTPUT_LEN_TM6144 LABRADOR_LDPC_OUTPUT_LEN(TM6144)
 #define LABRADOR_LDPC_OUTPUT_LEN_TM6140 LABRADOR_LDPC_OUTPUT_LEN(TM6144)
 #define LABRADOR_LDPC_OUTPUT_LEN_TM8192 LABRADOR_LDPC_OUTPUT_LEN(TM8192)
+#define LABRADOR_LDPC_OUTPUT_LEN_TM20480 LABRADOR_LDPC_OUTPUT_LEN(TM20480)
+#define LABRADOR_LDPC_OUTPUT_LEN_TM24576 LABRADOR_LDPC_OUTPUT_LEN(TM24576)
+#define LABRADOR_LDPC_OUTPUT_LEN_TM32768 LABRADOR_LDPC_OUTPUT_LEN(TM32768)
 
 /* ===========================================================================
  * Part 1 -- the reference's 21 entry points (single codeword per call).
@@ -421,7 +453,8 @@ uint32_t labrador_ldpc_edge_table_crc(enum labrador_ldpc_code code);
  * sparse parity-check matrix and one derived M x M inverse, TC codes through a table of per-byte parity
  * contributions.  This call computes the (n-k)/8 parity bytes of one data block (k/8 bytes) both ways on the host:
  * parity_tables from the very tables the kernels use, parity_generator by the reference's algorithm.
- * Returns 0, or a negative error if a table could not be derived or its two forms disagree. */
+ * Returns 0, or a negative error if a table could not be derived or its two forms disagree.  For the k = 16384 codes,
+ * which have no generator, it returns 1 and writes parity_tables only (parity_generator may be NULL). */
 int labrador_ldpc_host_encode_model(enum labrador_ldpc_code code, const uint8_t *data, uint8_t *parity_tables,
                                     uint8_t *parity_generator);
 

@@ -189,6 +189,11 @@ class LDPCCode(enum.IntEnum):
     TM5120 = 6
     TM6144 = 7
     TM8192 = 8
+    # extension: the k = 16384 codes whose parity-check constants the reference carries without supporting them
+    # (src/lib.rs:81-83); see include/labrador_ldpc.h
+    TM20480 = 9
+    TM24576 = 10
+    TM32768 = 11
 
     # ---- parameters (reference src/codes/mod.rs:367-409, src/decoder.rs:93-116) ----
     def n(self): return int(lib.labrador_ldpc_code_n(int(self)))

@@ -528,9 +528,14 @@ unsigned long long labrador_ldpc_kernel_launch_count(void) { return launch_count
 int labrador_ldpc_host_encode_model(enum labrador_ldpc_code code, const uint8_t *data, uint8_t *parity_tables,
                                     uint8_t *parity_generator) {
     if (!ldpc::code_info((int)code)) return LABRADOR_LDPC_ERR_BAD_CODE;
-    if (!data || !parity_tables || !parity_generator) return LABRADOR_LDPC_ERR_NULL_POINTER;
-    ldpc::host_encode_generator((int)code, data, parity_generator);
-    return ldpc::host_encode_tables((int)code, data, parity_tables) ? 0 : LABRADOR_LDPC_ERR_BAD_ARGUMENT;
+    if (!data || !parity_tables) return LABRADOR_LDPC_ERR_NULL_POINTER;
+    const bool has_gen = ldpc::code_info((int)code)->gen != nullptr;
+    if (has_gen) {
+        if (!parity_generator) return LABRADOR_LDPC_ERR_NULL_POINTER;
+        ldpc::host_encode_generator((int)code, data, parity_generator);
+    }
+    if (!ldpc::host_encode_tables((int)code, data, parity_tables)) return LABRADOR_LDPC_ERR_BAD_ARGUMENT;
+    return has_gen ? 0 : 1;      // 1: k = 16384 code -- no generator exists, parity_generator was not written
 }
 
 const char *labrador_ldpc_decode_ms_kernel_name(enum labrador_ldpc_code code, int llr_type) {

@@ -52,9 +52,9 @@ __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restric
             for (int c = tid; c < nc; c += nt) {
                 int par = 0, er = 0;
                 for (int j = 0; j < dc; j++) {
-                    const uint32_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
-                    if (ent == kNoEdge) break;
-                    const int var = ent >> 16;
+                    const uint64_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
+                    if (ent == kNoEdge64) break;
+                    const int var = (int)(ent >> 32);
                     if (var >= n) er++;
                     else par ^= bits[var];
                 }
@@ -65,9 +65,9 @@ __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restric
             for (int a = n + tid; a < nv; a += nt) {
                 int votes = 0;
                 for (int j = 0; j < dv; j++) {
-                    const uint32_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
-                    if (ent == kNoEdge) break;
-                    const int cp = cpar[ent >> 16];
+                    const uint64_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
+                    if (ent == kNoEdge64) break;
+                    const int cp = cpar[(int)(ent >> 32)];
                     if (cp & 2) votes += (cp & 1) ? 1 : -1;
                 }
                 if (votes > 0) bits[a] = 1;
@@ -81,9 +81,9 @@ __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restric
             for (int c = tid; c < nc; c += nt) {                         // :269-273
                 int par = 0;
                 for (int j = 0; j < dc; j++) {
-                    const uint32_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
-                    if (ent == kNoEdge) break;
-                    par ^= bits[ent >> 16];
+                    const uint64_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
+                    if (ent == kNoEdge64) break;
+                    par ^= bits[(int)(ent >> 32)];
                 }
                 cpar[c] = (uint8_t)par;
             }
@@ -93,9 +93,9 @@ __global__ void decode_bf_kernel(const DeviceCode code, const uint8_t *__restric
             for (int a = tid; a < nv; a += nt) {
                 int viol = 0;
                 for (int j = 0; j < dv; j++) {
-                    const uint32_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
-                    if (ent == kNoEdge) break;
-                    viol += cpar[ent >> 16];
+                    const uint64_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
+                    if (ent == kNoEdge64) break;
+                    viol += cpar[(int)(ent >> 32)];
                 }
                 cnt[a] = (uint8_t)viol;
                 seen |= 1u << viol;
@@ -142,7 +142,8 @@ cudaError_t launch_decode_bf(DeviceCtx &ctx, int code, const uint8_t *input, uin
     const DeviceCode &dc = ctx.codes[code];
     const size_t smem = (size_t)dc.vars * 2 + dc.checks;
     int threads = dc.vars < 512 ? ((dc.vars + 31) / 32) * 32 : 512;
-    cudaError_t err = cudaFuncSetAttribute(decode_bf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t err = cudaFuncSetAttribute(decode_bf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(smem > 64 * 1024 ? smem : 64 * 1024));
     if (err != cudaSuccess) return err;
     unsigned long long grid = batch > 0x7FFFFFFFull ? 0x7FFFFFFFull : batch;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;

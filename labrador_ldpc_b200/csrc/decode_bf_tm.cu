@@ -312,9 +312,16 @@ cudaError_t launch_bf_tm(DeviceCtx &ctx, const CodeInfo &c, const uint8_t *input
 // Returns true (and launches) for the TM codes.
 bool launch_decode_bf_tm(DeviceCtx &ctx, int code, const uint8_t *input, uint8_t *output, size_t batch,
                          size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err) {
-    if (code < 3 || code > 8) return false;
+    if (code < 3 || code >= kNumCodes) return false;
     const CodeInfo &c = *code_info(code);
     switch (code) {
+        // the k = 16384 codes: same prototypes, M = 2048 / 4096 / 8192 (two / four / eight words per lane)
+        case 9: if (!structure_matches<2>(c) || c.m != 2048) return false;
+                *err = launch_bf_tm<2, 2048>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
+        case 10: if (!structure_matches<1>(c) || c.m != 4096) return false;
+                *err = launch_bf_tm<1, 4096>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
+        case 11: if (!structure_matches<0>(c) || c.m != 8192) return false;
+                *err = launch_bf_tm<0, 8192>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
         case 3: if (!structure_matches<2>(c) || c.m != 128) return false;
                 *err = launch_bf_tm<2, 128>(ctx, c, input, output, batch, max_iters, success, iters, stream); return true;
         case 4: if (!structure_matches<1>(c) || c.m != 256) return false;

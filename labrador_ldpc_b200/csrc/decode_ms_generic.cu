@@ -31,7 +31,8 @@ constexpr int kMaxVarDeg = 6;
 struct MsLayout {
     // byte offsets into dynamic shared memory
     unsigned v_off, min1_off, min2_off, llr_off, sgn_off, hb_off, total;
-    bool v_in_smem, llr_in_smem;
+    bool v_in_smem, mm_in_smem, llr_in_smem;
+    unsigned slot_elems;      // elements of T per persistent CTA in the global scratch: v (edges) and / or min1, min2 (2 * checks)
 };
 
 template <class T, int FRONT = kFrontNone>
@@ -43,10 +44,11 @@ decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay,
                          T *__restrict__ vscratch, const float fscale, const float flimit) {
     typedef Arith<T> A;
     extern __shared__ __align__(16) unsigned char smem[];
-    T *v = lay.v_in_smem ? reinterpret_cast<T *>(smem + lay.v_off)
-                         : vscratch + (size_t)blockIdx.x * code.edges;
-    T *min1 = reinterpret_cast<T *>(smem + lay.min1_off);
-    T *min2 = reinterpret_cast<T *>(smem + lay.min2_off);
+    T *slot = vscratch + (size_t)blockIdx.x * lay.slot_elems;
+    T *v = lay.v_in_smem ? reinterpret_cast<T *>(smem + lay.v_off) : slot;
+    T *mm = slot + (lay.v_in_smem ? 0 : code.edges);
+    T *min1 = lay.mm_in_smem ? reinterpret_cast<T *>(smem + lay.min1_off) : mm;
+    T *min2 = lay.mm_in_smem ? reinterpret_cast<T *>(smem + lay.min2_off) : mm + code.checks;
     T *llr_s = reinterpret_cast<T *>(smem + lay.llr_off);
     uint8_t *sgn = smem + lay.sgn_off;
     uint8_t *hb = smem + lay.hb_off;
@@ -80,9 +82,9 @@ decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay,
                 for (int j = 0; j < kMaxVarDeg; j++) {
                     ul[j] = A::zero(); vold[j] = A::zero();
                     if (j < dv) {
-                        const uint32_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
-                        if (ent != kNoEdge) {
-                            const int idx = ent & 0xFFFF, c = ent >> 16;
+                        const uint64_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
+                        if (ent != kNoEdge64) {
+                            const int idx = (int)(uint32_t)ent, c = (int)(ent >> 32);
                             const T vv = v[idx];
                             T u = (A::abs(vv) == min1[c]) ? min2[c] : min1[c];   // :391-395
                             if (sgn[c]) u = A::neg(u);                           // :398-400
@@ -95,9 +97,9 @@ decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay,
 #pragma unroll
                 for (int j = 0; j < kMaxVarDeg; j++) {
                     if (j < dv) {
-                        const uint32_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
-                        if (ent != kNoEdge) {
-                            const int idx = ent & 0xFFFF;
+                        const uint64_t ent = __ldg(code.var_tab + (size_t)j * nv + a);
+                        if (ent != kNoEdge64) {
+                            const int idx = (int)(uint32_t)ent;
                             const T nvv = A::sat_sub(va, ul[j]);                 // :421
                             const bool keep = (A::hard_bit(nvv) == A::hard_bit(vold[j])) || (vold[j] == A::zero());
                             v[idx] = keep ? nvv : A::zero();                     // :422-426
@@ -113,9 +115,9 @@ decode_ms_generic_kernel(const DeviceCode code, const MsLayout lay,
                 T m1 = A::maxval(), m2 = A::maxval();                       // :414-415
                 int s = 0, par = 0;
                 for (int j = 0; j < dc; j++) {
-                    const uint32_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
-                    if (ent == kNoEdge) break;
-                    const int idx = ent & 0xFFFF, var = ent >> 16;
+                    const uint64_t ent = __ldg(code.chk_tab + (size_t)j * nc + c);
+                    if (ent == kNoEdge64) break;
+                    const int idx = (int)(uint32_t)ent, var = (int)(ent >> 32);
                     const T vv = v[idx];
                     const T av = A::abs(vv);
                     if (av < m1) { m2 = m1; m1 = av; }                      // :430-435
@@ -153,15 +155,22 @@ template <class T>
 MsLayout make_layout(const DeviceCode &c, int max_smem) {
     MsLayout l{};
     const unsigned ts = sizeof(T);
-    const unsigned fixed = align16(c.checks * ts) * 2 + align16(c.checks) + align16(c.vars);
+    // per-check sign bytes and per-variable hard-decision bytes always sit in shared memory; the per-check minima, the
+    // messages and the LLRs join them in this order as far as they fit (the k = 16384 codes keep f32 / f64 minima, and
+    // every code beyond TM2048 its messages, in an L2-resident slot per persistent CTA)
+    const unsigned base = align16(c.checks) + align16(c.vars);
+    const unsigned mbytes = align16(c.checks * ts) * 2;
     const unsigned vbytes = align16(c.edges * ts);
     const unsigned lbytes = align16(c.n * ts);
-    l.v_in_smem = fixed + vbytes <= (unsigned)max_smem;
+    l.mm_in_smem = base + mbytes <= (unsigned)max_smem;
+    const unsigned fixed = base + (l.mm_in_smem ? mbytes : 0);
+    l.v_in_smem = l.mm_in_smem && fixed + vbytes <= (unsigned)max_smem;
     l.llr_in_smem = fixed + (l.v_in_smem ? vbytes : 0) + lbytes <= (unsigned)max_smem;
+    l.slot_elems = (l.v_in_smem ? 0u : (unsigned)c.edges) + (l.mm_in_smem ? 0u : 2u * (unsigned)c.checks);
     unsigned off = 0;
     l.v_off = off; if (l.v_in_smem) off += vbytes;
-    l.min1_off = off; off += align16(c.checks * ts);
-    l.min2_off = off; off += align16(c.checks * ts);
+    l.min1_off = off; if (l.mm_in_smem) off += align16(c.checks * ts);
+    l.min2_off = off; if (l.mm_in_smem) off += align16(c.checks * ts);
     l.llr_off = off; if (l.llr_in_smem) off += lbytes;
     l.sgn_off = off; off += align16(c.checks);
     l.hb_off = off; off += align16(c.vars);
@@ -184,7 +193,7 @@ cudaError_t launch_generic(DeviceCtx &ctx, int code, const void *llrs, uint8_t *
         // persistent CTAs, one global message slot each
         grid = (unsigned long long)ctx.sm_count;
         if (grid > batch) grid = batch;
-        const size_t need = (size_t)grid * dc.edges * sizeof(T);
+        const size_t need = (size_t)grid * lay.slot_elems * sizeof(T);
         if (ctx.vscratch_bytes < need) {
             if (ctx.vscratch) cudaFree(ctx.vscratch);
             ctx.vscratch = nullptr; ctx.vscratch_bytes = 0;

@@ -541,10 +541,11 @@ cudaError_t launch_encode(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t
     // TM codes: through the sparse parity-check matrix (encode_tm.cu), 4-16x fewer bit operations than the generator;
     // LABRADOR_LDPC_ENC_GENERATOR=1 keeps the generator kernel below for A/B runs and tests
     static const bool force_gen = [] { const char *e = getenv("LABRADOR_LDPC_ENC_GENERATOR"); return e && atoi(e) != 0; }();
-    if (!force_gen) {
+    if (!force_gen || !dc.gen) {
         cudaError_t err = cudaSuccess;
         if (launch_encode_tm(ctx, code, data, codewords, batch, stream, &err)) return err;
     }
+    if (!dc.gen) return cudaErrorNotSupported;      // k = 16384 codes: no generator exists, the sparse-H encoder is the only one
     // TC codes: one codeword per thread over a nibble / byte lookup table, at every batch size (filling the table is
     // hidden by the launch: tools/enc_crossover.py).  The generator kernel below remains as the A/B reference.
     if (!force_gen && code < 3 && dc.enc_tc_lut) {

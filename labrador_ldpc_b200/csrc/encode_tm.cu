@@ -379,11 +379,19 @@ cudaError_t launch_enc_tm(DeviceCtx &ctx, const CodeInfo &c, const DeviceCode &d
 // Returns true (and launches) for the TM codes whose parity-check-based encoder table exists.
 bool launch_encode_tm(DeviceCtx &ctx, int code, const uint8_t *data, uint8_t *codewords, size_t batch,
                       cudaStream_t stream, cudaError_t *err) {
-    if (code < 3 || code > 8) return false;
+    if (code < 3 || code >= kNumCodes) return false;
     const DeviceCode &dc = ctx.codes[code];
     if (!dc.enc_ainv) return false;
     const CodeInfo &c = *code_info(code);
     switch (code) {
+        // the k = 16384 codes (no generator exists for them in the reference: this is their only encoder).  The nibble
+        // table of M = 4096 / 8192 would not fit in shared memory, so all three use the compact form.
+        case 9: if (!structure_matches<2>(c) || c.m != 2048) return false;
+                *err = launch_enc_tm_form<2, 2048, false>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 10: if (!structure_matches<1>(c) || c.m != 4096) return false;
+                *err = launch_enc_tm_form<1, 4096, false>(ctx, c, dc, data, codewords, batch, stream); return true;
+        case 11: if (!structure_matches<0>(c) || c.m != 8192) return false;
+                *err = launch_enc_tm_form<0, 8192, false>(ctx, c, dc, data, codewords, batch, stream); return true;
         case 3: if (!structure_matches<2>(c) || c.m != 128) return false;
                 *err = launch_enc_tm<2, 128>(ctx, c, dc, data, codewords, batch, stream); return true;
         case 4: if (!structure_matches<1>(c) || c.m != 256) return false;

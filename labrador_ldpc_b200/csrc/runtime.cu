@@ -91,9 +91,10 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
     std::vector<unsigned char> blob;
     struct Off { size_t var_tab, chk_tab, gen, gen32, ainv, lut, tc_lut; bool has_ainv, has_tc_lut; };
     Off offs[kNumCodes];
+    bool has_lut_of[kNumCodes] = {};
     for (int ci = 0; ci < kNumCodes; ci++) {
         const CodeInfo &c = *code_info(ci);
-        std::vector<uint32_t> vt, ct;
+        std::vector<uint64_t> vt, ct;
         build_ell_tables(c, vt, ct);
         auto append = [&blob](const void *p, size_t bytes) {
             const size_t off = align_up(blob.size(), 256);
@@ -101,9 +102,9 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
             memcpy(blob.data() + off, p, bytes);
             return off;
         };
-        offs[ci].var_tab = append(vt.data(), vt.size() * 4);
-        offs[ci].chk_tab = append(ct.data(), ct.size() * 4);
-        const size_t gwords = (size_t)(c.k / c.b) * ((c.n - c.k) / 64);
+        offs[ci].var_tab = append(vt.data(), vt.size() * 8);
+        offs[ci].chk_tab = append(ct.data(), ct.size() * 8);
+        const size_t gwords = c.gen ? (size_t)(c.k / c.b) * ((c.n - c.k) / 64) : 0;
         offs[ci].gen = append(c.gen, gwords * 8);
         std::vector<uint32_t> g32(gwords * 2);
         for (size_t i = 0; i < gwords; i++) {
@@ -115,10 +116,13 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         offs[ci].has_ainv = tm_encoder_table(ci, ainv);
         offs[ci].ainv = offs[ci].has_ainv ? append(ainv.data(), ainv.size() * 4) : 0;
         std::vector<uint32_t> tc_lut;
-        offs[ci].has_tc_lut = (ci == 1 || ci == 2) ? tc_rot_encoder_lut(ci, tc_lut) : tc_encoder_lut(ci, tc_encoder_group_bits(ci), tc_lut);
+        offs[ci].has_tc_lut = c.gen && ((ci == 1 || ci == 2) ? tc_rot_encoder_lut(ci, tc_lut) : tc_encoder_lut(ci, tc_encoder_group_bits(ci), tc_lut));
         offs[ci].tc_lut = offs[ci].has_tc_lut ? append(tc_lut.data(), tc_lut.size() * 4) : 0;
         std::vector<uint32_t> lut;
-        offs[ci].lut = (offs[ci].has_ainv && tm_encoder_lut(ci, lut)) ? append(lut.data(), lut.size() * 4) : 0;
+        // the nibble lookup table is 512 rows of M bits: it fits the shared memory of a CTA up to M = 2048
+        const bool has_lut = offs[ci].has_ainv && c.m <= 2048 && tm_encoder_lut(ci, lut);
+        has_lut_of[ci] = has_lut;
+        offs[ci].lut = has_lut ? append(lut.data(), lut.size() * 4) : 0;
     }
     CUDA_TRY(cudaMalloc(&ctx->table_blob, blob.size()));
     CUDA_TRY(cudaMemcpy(ctx->table_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -130,13 +134,13 @@ int build_ctx(int device, std::unique_ptr<DeviceCtx> &out) {
         d.edges = c.edges; d.checks = c.checks; d.vars = c.vars;
         d.max_var_degree = c.max_var_degree; d.max_check_degree = c.max_check_degree;
         d.n_blocks = c.n_blocks;
-        d.var_tab = reinterpret_cast<const uint32_t *>(base + offs[ci].var_tab);
-        d.chk_tab = reinterpret_cast<const uint32_t *>(base + offs[ci].chk_tab);
-        d.gen = reinterpret_cast<const uint64_t *>(base + offs[ci].gen);
-        d.gen32 = reinterpret_cast<const uint32_t *>(base + offs[ci].gen32);
+        d.var_tab = reinterpret_cast<const uint64_t *>(base + offs[ci].var_tab);
+        d.chk_tab = reinterpret_cast<const uint64_t *>(base + offs[ci].chk_tab);
+        d.gen = c.gen ? reinterpret_cast<const uint64_t *>(base + offs[ci].gen) : nullptr;
+        d.gen32 = c.gen ? reinterpret_cast<const uint32_t *>(base + offs[ci].gen32) : nullptr;
         d.enc_ainv = offs[ci].has_ainv ? reinterpret_cast<const uint32_t *>(base + offs[ci].ainv) : nullptr;
         d.enc_tc_lut = offs[ci].has_tc_lut ? reinterpret_cast<const uint32_t *>(base + offs[ci].tc_lut) : nullptr;
-        d.enc_lut = offs[ci].has_ainv ? reinterpret_cast<const uint32_t *>(base + offs[ci].lut) : nullptr;
+        d.enc_lut = has_lut_of[ci] ? reinterpret_cast<const uint32_t *>(base + offs[ci].lut) : nullptr;
     }
     out = std::move(ctx);
     return LDPC_OK;

@@ -49,9 +49,9 @@ struct DeviceCode {
     int edges, checks, vars;
     int max_var_degree, max_check_degree;
     int n_blocks;
-    const uint32_t *var_tab;   // [max_var_degree][vars]   idx | check << 16
-    const uint32_t *chk_tab;   // [max_check_degree][checks] idx | var << 16
-    const uint64_t *gen;       // compact generator rows
+    const uint64_t *var_tab;   // [max_var_degree][vars]   idx | check << 32
+    const uint64_t *chk_tab;   // [max_check_degree][checks] idx | var << 32
+    const uint64_t *gen;       // compact generator rows (nullptr for the k = 16384 codes, which the reference does not encode)
     const uint32_t *gen32;     // same rows as big-endian-ordered 32-bit words
     const uint32_t *enc_ainv;  // TM codes: first columns of the circulants of A^-1 (code_tables.h: tm_encoder_table), else null
     const uint32_t *enc_tc_lut; // TC codes: byte (TC128, TC256) / nibble (TC512) table of parity contributions, else null

@@ -49,7 +49,7 @@ struct Params {
     const uint64_t *gen;
 };
 
-const Params PARAMS[9] = {
+const Params PARAMS[12] = {
     {128, 64, 0, 16, 16, 512, ccsds_proto_tc128, nullptr, ccsds_gen_tc128},
     {256, 128, 0, 32, 32, 1024, ccsds_proto_tc256, nullptr, ccsds_gen_tc256},
     {512, 256, 0, 64, 64, 2048, ccsds_proto_tc512, nullptr, ccsds_gen_tc512},
@@ -59,9 +59,17 @@ const Params PARAMS[9] = {
     {5120, 4096, 512, 512, 128, 19968, ccsds_proto_tm_r45, ccsds_phi_m512, ccsds_gen_tm5120},
     {6144, 4096, 1024, 1024, 256, 23552, ccsds_proto_tm_r23, ccsds_phi_m1024, ccsds_gen_tm6144},
     {8192, 4096, 2048, 2048, 512, 30720, ccsds_proto_tm_r12, ccsds_phi_m2048, ccsds_gen_tm8192},
+    // The k = 16384 codes.  The reference has their parity-check constants (compact_parity_checks.rs:84-96; the phi
+    // tables for M = 4096 / 8192 are selected at src/codes/mod.rs:473-476) but no enum variant, parameters or
+    // generators (src/lib.rs:81-83).  Parameters below follow the pattern of the six TM codes above (p = M, b = M/4,
+    // edges = blocks * M); the decoders are the same code run over these parameters; there is no encoder (gen ==
+    // nullptr) and NO reference golden of any kind for them -- see tests/test_gpu_k16384.py for how they are pinned.
+    {20480, 16384, 2048, 2048, 512, 39 * 2048, ccsds_proto_tm_r45, ccsds_phi_m2048, nullptr},
+    {24576, 16384, 4096, 4096, 1024, 23 * 4096, ccsds_proto_tm_r23, ccsds_phi_m4096, nullptr},
+    {32768, 16384, 8192, 8192, 2048, 15 * 8192, ccsds_proto_tm_r12, ccsds_phi_m8192, nullptr},
 };
 
-inline bool valid(int code) { return code >= 0 && code < 9; }
+inline bool valid(int code) { return code >= 0 && code < 12; }
 
 // src/decoder.rs:93-116
 inline size_t bf_working_len(const Params &c) { return c.n + c.p; }
@@ -546,6 +554,7 @@ int oracle_edges(int code, uint32_t *checks, uint32_t *vars, uint32_t *crc_out) 
 int oracle_copy_encode(int code, const uint8_t *data, uint8_t *codeword, int word) {
     if (!valid(code)) return -1;
     const Params &c = PARAMS[code];
+    if (!c.gen) return -2;      // no generator: the reference cannot encode this code
     memmove(codeword, data, c.k / 8);
     if (word == 8) {
         encode_parity_u8(c, codeword, codeword + c.k / 8);
@@ -567,6 +576,7 @@ int oracle_copy_encode_batch(int code, const uint8_t *data, uint8_t *codewords, 
                              int nthreads) {
     if (!valid(code)) return -1;
     const Params &c = PARAMS[code];
+    if (!c.gen) return -2;      // no generator: the reference cannot encode this code
     parallel_frames(batch, nthreads, [&](size_t b0, size_t b1, int) {
         for (size_t f = b0; f < b1; f++) {
             uint8_t *cw = codewords + f * (c.n / 8);

@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CODES = ["TC128", "TC256", "TC512", "TM1280", "TM1536", "TM2048", "TM5120", "TM6144", "TM8192"]
+CODES = ["TC128", "TC256", "TC512", "TM1280", "TM1536", "TM2048", "TM5120", "TM6144", "TM8192",
+         "TM20480", "TM24576", "TM32768"]      # the last three: k = 16384, decode only (oracle.cpp PARAMS)
 
 _DT = {
     "i8": (np.int8, ctypes.c_int8),

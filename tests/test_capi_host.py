@@ -46,7 +46,7 @@ def test_size_getters_match_reference_table(ldpc, kats):
         assert c.decode_ms_working_len() == P["decode_ms_working_len"]
         assert c.decode_ms_working_u8_len() == P["decode_ms_working_u8_len"]
         assert c.output_len() == P["output_len"]
-    assert ldpc.lib.labrador_ldpc_code_n(9) == 0 and ldpc.lib.labrador_ldpc_code_n(-1) == 0
+    assert ldpc.lib.labrador_ldpc_code_n(12) == 0 and ldpc.lib.labrador_ldpc_code_n(-1) == 0
 
 
 def test_edge_table_crc_goldens(ldpc, kats):
@@ -84,7 +84,49 @@ def test_encoder_tables_against_generator_and_oracle(ldpc, kats):
             assert np.array_equal(pt, want), (names[code], i, "table model")
             if i == 0:
                 assert pt.tolist() == kats["encode_parity"][names[code]]
-    assert L.labrador_ldpc_host_encode_model(9, cases[0].ctypes.data, pt.ctypes.data, pg.ctypes.data) < 0
+    assert L.labrador_ldpc_host_encode_model(12, cases[0].ctypes.data, pt.ctypes.data, pg.ctypes.data) < 0
+
+
+def test_k16384_codes_tables_and_sparse_encoder(ldpc):
+    """The three k = 16384 codes (extension; the reference has their parity-check constants but no parameters, no
+    generators and therefore NO golden of any kind).  What can be pinned on the host: the oracle and the product expand
+    the same edge list (CRC), the degrees follow the prototypes, and the product's sparse-H encoder tables produce
+    codewords that satisfy every parity check of the ORACLE's edge list -- H c = 0 with the data bits in place is the
+    definition of the systematic encoder, and the parity part of H is invertible, so the answer is unique."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    oracle = pyoracle.Oracle()
+    L = ldpc.lib
+    L.labrador_ldpc_host_encode_model.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.labrador_ldpc_host_encode_model.restype = ctypes.c_int
+    rng = np.random.default_rng(11)
+    expect = {9: (20480, 16384, 2048, 2048, 39), 10: (24576, 16384, 4096, 4096, 23), 11: (32768, 16384, 8192, 8192, 15)}
+    for code, (n, k, p, m, blocks) in expect.items():
+        c = ldpc.LDPCCode(code)
+        assert (c.n(), c.k(), c.punctured_bits(), c.paritycheck_sum()) == (n, k, p, blocks * m)
+        assert (oracle.n(code), oracle.k(code), oracle.p(code), oracle.m(code)) == (n, k, p, m)
+        assert c.output_len() == (n + p) // 8 and c.decode_ms_working_len() == 2 * blocks * m + 3 * n + 3 * p - 2 * k
+        cnt, checks, vars_, crc = oracle.edges(code)
+        assert cnt == blocks * m and crc == c.edge_table_crc()
+        # check degrees 3 (row 0) and 2 * (blocks - 3) / 2 ... as in the smaller code of the same rate
+        deg_c = np.bincount(checks, minlength=n + p - k)
+        small = {9: 6, 10: 7, 11: 8}[code]
+        _, ch_s, _, _ = oracle.edges(small)
+        assert sorted(set(deg_c.tolist())) == sorted(set(np.bincount(ch_s).tolist()))
+        kb, pb = k // 8, (n - k) // 8
+        for data in (rng.integers(0, 256, kb, dtype=np.uint8), np.zeros(kb, np.uint8), (np.arange(kb) % 256).astype(np.uint8)):
+            pt = np.zeros(pb, np.uint8)
+            assert L.labrador_ldpc_host_encode_model(code, data.ctypes.data, pt.ctypes.data, None) == 1
+            tx = np.unpackbits(np.concatenate([data, pt]))                # the n transmitted bits
+            # punctured bits: row 2 is [data terms] + S(CB) + I(CC), so bit j of CC = parity of the row-2 check over the rest
+            bits = np.concatenate([tx, np.zeros(p, np.uint8)])
+            row2 = (checks >= 2 * m) & (vars_ < n)
+            par2 = np.bincount(checks[row2] - 2 * m, weights=bits[vars_[row2]], minlength=m).astype(np.int64) & 1
+            bits[n:] = par2
+            syn = np.bincount(checks, weights=bits[vars_], minlength=n + p - k).astype(np.int64) & 1
+            assert not syn.any(), (code, int(syn.sum()))
+            if not data.any():
+                assert not pt.any()
 
 
 def test_header_macros_compile_and_match(kats, tmp_path):
@@ -190,7 +232,7 @@ def test_argument_validation_needs_no_gpu(ldpc):
     L = ldpc.lib
     buf = np.zeros(64, np.uint8)
     p = buf.ctypes.data
-    assert L.labrador_ldpc_decode_ms_i8_batch(9, p, p, 1, 10, p, None) == -1      # bad code
+    assert L.labrador_ldpc_decode_ms_i8_batch(12, p, p, 1, 10, p, None) == -1     # bad code
     assert L.labrador_ldpc_decode_ms_i8_batch(0, None, p, 1, 10, p, None) == -2   # null pointer
     assert L.labrador_ldpc_decode_ms_i8_batch(0, None, None, 0, 10, None, None) == 0  # empty batch is a no-op
     assert L.labrador_ldpc_decode_bf_batch(-1, p, p, 1, 10, p, None) == -1
@@ -203,7 +245,7 @@ def test_argument_validation_needs_no_gpu(ldpc):
     assert L.labrador_ldpc_decode_ms_i16_soft_batch(0, p, 4.0, 32768, p, 1, 10, p, None) == -5
     assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, p, float("inf"), 31, p, 1, 10, p, None) == -5
     assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, p, float("nan"), 31, p, 1, 10, p, None) == -5
-    assert L.labrador_ldpc_decode_ms_i8_soft_batch(9, p, 4.0, 31, p, 1, 10, p, None) == -1
+    assert L.labrador_ldpc_decode_ms_i8_soft_batch(12, p, 4.0, 31, p, 1, 10, p, None) == -1
     assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, None, 4.0, 31, p, 1, 10, p, None) == -2
     assert L.labrador_ldpc_decode_ms_i8_soft_batch(0, None, 4.0, 31, None, 0, 10, None, None) == 0
     assert L.labrador_ldpc_decode_ms_front_batch_async(0, 3, 1, p, 4.0, 31, p, 1, 10, p, None, None) == -5   # soft -> f32
@@ -230,7 +272,7 @@ def test_harness_kernel_argument_validation(ldpc):
     L = ldpc.lib
     buf = np.zeros(64, np.uint8)
     p = buf.ctypes.data
-    assert L.labrador_ldpc_random_data_batch(9, 1, 0, p, 1) == -1
+    assert L.labrador_ldpc_random_data_batch(12, 1, 0, p, 1) == -1
     assert L.labrador_ldpc_random_data_batch(0, 1, 0, None, 1) == -2
     assert L.labrador_ldpc_random_data_batch(0, 1, 0, None, 0) == 0
     assert L.labrador_ldpc_awgn_batch(0, 2, p, 1.0, 1.0, 31, 1, 0, p, 1) == -5          # i32 output
