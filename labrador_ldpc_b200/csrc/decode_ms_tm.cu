@@ -249,7 +249,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
     constexpr int NV = NCOL * M, N = (NCOL - 1) * M, NC = NROW * M;
     constexpr int HBW = NV / 32;           // hard-decision words
     constexpr int SYW = NC / 32;           // syndrome words
-    static_assert(S >= 32 && S % 32 == 0, "lane pairing needs at least one warp per half quarter");
+    // the ballot-packed hard bits (exit test without KNOBS bit 5) need a whole warp per half quarter; with the in-thread
+    // exit test only the rare second stage packs bits, and does it with atomics when S < 32 (TM1280: M = 128, S = 16)
+    static_assert((KNOBS & 32) != 0 ? (S >= 16 && NT % 32 == 0) : (S >= 32 && S % 32 == 0),
+                  "lane pairing needs at least one warp per half quarter");
     static_assert(SYW <= NT, "one thread per syndrome word");
     // Two-stage exit test.  Row 0 of every TM prototype is {I at column CA, I and P at the punctured column CP}.
     // Stage 1 (every iteration) packs the hard bits of those two columns only and tests the M row-0 checks; a
@@ -393,11 +396,18 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                     static_for<0, NCOL>([&](auto ci) {
                         constexpr int c = decltype(ci)::value;
                         const uint32_t g = gat[c / 2][wi] >> ((c & 1) * 8);             // bit 7 / 23: marginal >= 0
-                        const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (g & 0x00000080u) == 0);
-                        const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (g & 0x00800000u) == 0);
-                        if (lane == 0) {
-                            hb[hbw[wi] + c * M / 32] = b0;
-                            hb[hbw[wi] + (c * M + S) / 32] = b1;
+                        if constexpr (S % 32 == 0) {
+                            const unsigned b0 = __ballot_sync(0xFFFFFFFFu, (g & 0x00000080u) == 0);
+                            const unsigned b1 = __ballot_sync(0xFFFFFFFFu, (g & 0x00800000u) == 0);
+                            if (lane == 0) {
+                                hb[hbw[wi] + c * M / 32] = b0;
+                                hb[hbw[wi] + (c * M + S) / 32] = b1;
+                            }
+                        } else {        // a warp spans several half quarters: every thread ORs its two bits in (hb[] zeroed first)
+                            const int wd = tid + wi * NT;
+                            const int e0 = c * M + (wd / S) * Q + (wd % S);
+                            if ((g & 0x00000080u) == 0) atomicOr(&hb[e0 >> 5], 1u << (e0 & 31));
+                            if ((g & 0x00800000u) == 0) atomicOr(&hb[(e0 + S) >> 5], 1u << ((e0 + S) & 31));
                         }
                     });
                     continue;
@@ -597,6 +607,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
             hb_complete = false;
             if (__syncthreads_or(synd != 0) == 0) {
                 // stage 2: row 0 is clean -- pack the other columns and test rows 1..NROW-1
+                if constexpr (PIGGY && S % 32 != 0) {
+                    for (int i = tid; i < HBW; i += NT) hb[i] = 0;
+                    __syncthreads();
+                }
                 flush_pack();
                 hb_complete = true;
                 __syncthreads();
@@ -611,6 +625,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
             pf_lap(pf_exit);
         }
         if (!hb_complete) {       // decoding failed: the output is the hard decision of the last marginals (:466-473)
+            if constexpr (PIGGY && S % 32 != 0) {
+                for (int i = tid; i < HBW; i += NT) hb[i] = 0;
+                __syncthreads();
+            }
             flush_pack();
             __syncthreads();
         }
@@ -759,14 +777,28 @@ cudaError_t launch_tm_front(const Front &front, DeviceCtx &ctx, const CodeInfo &
     return cudaErrorInvalidValue;
 }
 
+bool has_decode_ms_tm_i8(int code);
+
 // Returns true (and launches) if a specialised kernel exists for (code, i8).
 bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch,
                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
                             cudaError_t *err, const Front &front) {
+    if (!has_decode_ms_tm_i8(code)) return false;
     const CodeInfo &c = *code_info(code);
     const void *l = llrs;
     const bool ff = front.kind != kFrontNone;
     switch (code) {
+        case 3:      // TM1280: M = 128, 64 threads per codeword; needs the in-thread exit test (S = 16 < one warp)
+            if (!structure_matches<2>(c) || c.m != 128) return false;
+            if (ff) *err = launch_tm_front<2, 128, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else {
+                // resident CTAs per SM the kernel is compiled for (register budget 65536 / 64 / MINB): LABRADOR_LDPC_TM1280_MINB
+                static const int minb = [] { const char *e = getenv("LABRADOR_LDPC_TM1280_MINB"); return e ? atoi(e) : 8; }();
+                if (minb <= 1) *err = launch_tm<2, 128, 1, 6, 32, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else if (minb <= 6) *err = launch_tm<2, 128, 1, 6, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else *err = launch_tm<2, 128, 1, 6, 32, 8>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            }
+            return true;
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
             if (ff) *err = launch_tm_front<1, 256, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -797,6 +829,9 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
     }
 }
 
-bool has_decode_ms_tm_i8(int code) { return code >= 4 && code <= 8; }
+bool has_decode_ms_tm_i8(int code) {
+    static const bool tm1280_wide = [] { const char *e = getenv("LABRADOR_LDPC_TM1280_WIDE"); return e && atoi(e) != 0; }();
+    return code >= (tm1280_wide ? 4 : 3) && code <= 8;      // LABRADOR_LDPC_TM1280_WIDE=1: TM1280 i8 stays on the scalar-lane kernel (A/B)
+}
 
 }  // namespace ldpc

@@ -349,7 +349,7 @@ namespace {
 size_t chunk_bytes_target() {
     static size_t v = [] {
         const char *e = getenv("LABRADOR_LDPC_CHUNK_MB");
-        size_t mb = e ? (size_t)atol(e) : 32;
+        size_t mb = e ? (size_t)atol(e) : 16;      // 16 MB: shortest fill and drain of the three-slot pipeline that still keeps PCIe busy (profiles/raw/r02d_chunk_sizes.txt)
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
