@@ -793,7 +793,7 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
             if (ff) *err = launch_tm_front<2, 128, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
             else {
                 // resident CTAs per SM the kernel is compiled for (register budget 65536 / 64 / MINB): LABRADOR_LDPC_TM1280_MINB
-                static const int minb = [] { const char *e = getenv("LABRADOR_LDPC_TM1280_MINB"); return e ? atoi(e) : 8; }();
+                static const int minb = [] { const char *e = getenv("LABRADOR_LDPC_TM1280_MINB"); return e ? atoi(e) : 6; }();
                 if (minb <= 1) *err = launch_tm<2, 128, 1, 6, 32, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 else if (minb <= 6) *err = launch_tm<2, 128, 1, 6, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 else *err = launch_tm<2, 128, 1, 6, 32, 8>(ctx, c, l, output, batch, max_iters, success, iters, stream);
