@@ -123,7 +123,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -134,12 +134,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
+    def wait_first(self, timeout_s=3.0):
+        """nvidia-smi needs a moment to start: block until its first sample so that short timed regions are covered."""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout_s:
+            time.sleep(0.01)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        # samples inside the timed region; a region shorter than the sampling period takes the samples around it
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 and len(r) >= 7] or \
+               [r for (t, r) in self.rows if t0 - 0.25 <= t <= t1 + 0.25 and len(r) >= 7] or \
+               [r for (_, r) in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm = sorted(float(r[0]) for r in rows)
@@ -492,11 +501,12 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    for _ in range(args.warmup):
+        step()
+    sampler.wait_first()
+    barrier()
     launches0 = L.kernel_launch_count()
     ev = lambda: torch.cuda.Event(enable_timing=True)
     starts = [ev() for _ in range(args.steps)]
@@ -602,7 +612,7 @@ def main():
             "what": "labrador_ldpc_copy_control_batch: the same arrays through the same chunked pipeline, no kernel"}
     if numa is not None:
         e2e_line["host_cores_local_to_gpu"] = numa
-    if world > 1 and spec[0]["op"] == "ms":
+    if world > 1 and wl == "c3":
         # the library's own multi-device split, driven by ONE process (rank 0) while the other ranks wait
         barrier()
         if rank == 0:

@@ -45,6 +45,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "bulk_copy.cuh"
 #include "front.cuh"
 #include "runtime.h"
 #include "tm_common.cuh"
@@ -62,30 +63,6 @@ __device__ __forceinline__ uint32_t prmt_sign7(uint32_t x) {
     return r;
 }
 __device__ __forceinline__ uint32_t lane_rot(uint32_t x, uint32_t sh) { return __funnelshift_l(x, x, sh); }
-
-// ---- bulk asynchronous copy (TMA, cp.async.bulk) of one frame's LLRs into shared memory ----
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra LAB_WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-// one thread: arm the barrier with the byte count and start the copy (dst, src and bytes are multiples of 16)
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order earlier generic-proxy reads of dst
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
 
 constexpr int kMaxDeg = 18;
 
@@ -320,7 +297,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
         const unsigned long long f0 = atomicAdd(counter, 1ull);
         s_frame[0] = f0;
         if (use_bulk && f0 < batch) bulk_load(stage, in_all + f0 * (unsigned long long)FB, FB, &s_bar[0]);

@@ -26,6 +26,7 @@
 #include <cstdlib>
 
 #include "biased_arith.cuh"
+#include "bulk_copy.cuh"
 #include "front.cuh"
 #include "runtime.h"
 #include "tm_common.cuh"
@@ -36,29 +37,6 @@ using namespace tm;
 namespace {
 
 constexpr int kMaxDeg16 = 18;
-
-__device__ __forceinline__ uint32_t smem_addr16(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init16(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr16(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait16(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra LAB_WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_addr16(bar)), "r"(parity) : "memory");
-}
-// one thread: arm the barrier with the byte count and start the bulk copy (TMA; dst, src and bytes are multiples of 16)
-__device__ __forceinline__ void bulk_load16(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr16(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr16(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr16(bar)) : "memory");
-}
 
 __device__ __forceinline__ uint32_t rot16(uint32_t x, uint32_t sh) { return __funnelshift_l(x, x, sh); }
 // bit 15 of each 16-bit lane -> lane mask
@@ -169,12 +147,12 @@ decode_ms_tm_i16_kernel(const TmParams prm, const typename FrontSrc<FRONT, int16
 
     const bool use_bulk = (reinterpret_cast<uintptr_t>(llrs_all) & 15u) == 0;
     if (tid == 0) {
-        mbar_init16(&s_bar[0], 1);
-        mbar_init16(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init_fence();
         const unsigned long long f0 = atomicAdd(counter, 1ull);
         s_frame[0] = f0;
-        if (use_bulk && f0 < batch) bulk_load16(stage, in_all + f0 * (unsigned long long)FB, FB, &s_bar[0]);
+        if (use_bulk && f0 < batch) bulk_load(stage, in_all + f0 * (unsigned long long)FB, FB, &s_bar[0]);
     }
     __syncthreads();
     unsigned cur = 0, bar_parity = 0;
@@ -186,11 +164,11 @@ decode_ms_tm_i16_kernel(const TmParams prm, const typename FrontSrc<FRONT, int16
             const unsigned long long fn = atomicAdd(counter, 1ull);
             s_frame[cur ^ 1] = fn;
             if (use_bulk && fn < batch)
-                bulk_load16(stage + (cur ^ 1) * FB, in_all + fn * (unsigned long long)FB, FB, &s_bar[cur ^ 1]);
+                bulk_load(stage + (cur ^ 1) * FB, in_all + fn * (unsigned long long)FB, FB, &s_bar[cur ^ 1]);
         }
         const Src *llr;
         if (use_bulk) {
-            mbar_wait16(&s_bar[cur], (bar_parity >> cur) & 1u);
+            mbar_wait(&s_bar[cur], (bar_parity >> cur) & 1u);
             bar_parity ^= 1u << cur;
             llr = reinterpret_cast<const Src *>(stage + cur * FB);
         } else {

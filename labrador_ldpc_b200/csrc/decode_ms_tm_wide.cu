@@ -4,7 +4,8 @@
 // Replaces LDPCCode::decode_ms::<T> (reference src/decoder.rs:347-475).  Same skeleton as
 // decode_ms_tm.cu -- thread t owns element t of every prototype column and every prototype row,
 // identity-block messages stay in registers, pi_k-block messages go through shared memory in check
-// order, u is never stored, two-stage bit-packed exit test -- with one value per 32-bit register.
+// order, u is never stored, two-stage exit test (row 0 in the threads that own its checks, rows 1-2 from bit-packed
+// hard decisions only when row 0 is clean) -- with one value per 32-bit register.
 // i8 / i16 use the biased one-instruction arithmetic of biased_arith.cuh; the other types the plain scalar
 // DecodeFrom semantics of llr_arith.cuh (reference src/decoder.rs:42-86):
 //   variable side  va = llr (+) u_0 (+) u_1 ...  in ascending edge index (:408), then v_j = va (-) u_j (:421)
@@ -60,6 +61,13 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ST *msg = reinterpret_cast<ST *>(smem_raw);                                 // [NP][M], check order
     uint32_t *hb = reinterpret_cast<uint32_t *>(smem_raw + sizeof(ST) * NP * M);   // [HBW] packed hard decisions
+    // Row 0 of every TM prototype is I(CA) + I(CP) + P(CP) (static_assert'ed in decode_ms_tm.cu): the two identity terms of
+    // a check are marginals of the thread that owns the check, the permuted one arrives through this message-shaped byte
+    // array (written with the address of block 2), so every thread tests its own row-0 checks inside the check phase.
+    uint8_t *hmsg = reinterpret_cast<uint8_t *>(hb + HBW);                         // [M] hard bits of column CP, permuted by block 2
+    constexpr int PS2 = count_p<P>(2);
+    static_assert(P::blk(2).row == 0 && P::blk(2).col == CP && P::blk(2).isp && !P::blk(0).isp && !P::blk(1).isp &&
+                  P::blk(0).col == CA && P::blk(1).col == CP && P::blk(3).row == 1, "row 0 must be I(CA) + I(CP) + P(CP)");
     __shared__ unsigned long long s_frame;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -116,18 +124,15 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
 
         unsigned iters_run = max_iters;
         bool ok = false, hb_complete = true;
-        uint32_t pack[EPT];
-        auto flush_pack = [&]() {      // ballot-pack the hard bits of the columns stage 1 skipped
+        uint32_t pack[EPT];            // hard bits of every column of the latest variable phase (column NCOL-1 at bit 0)
+        bool hloc[EPT], bad[EPT];      // XOR of the two in-thread terms of the thread's row-0 check; its parity
+        auto flush_pack = [&]() {      // ballot-pack the hard bits of all columns (second stage / output)
 #pragma unroll
             for (int ei = 0; ei < EPT; ei++) {
-                int kpos = 0;
                 static_for<0, NCOL>([&](auto ci) {
                     constexpr int c = NCOL - 1 - decltype(ci)::value;
-                    if constexpr (c != CA && c != CP) {
-                        const unsigned bw = __ballot_sync(0xFFFFFFFFu, (pack[ei] >> kpos) & 1u);
-                        if (lane == 0) hb[(c * M + tid + ei * NT) >> 5] = bw;
-                        kpos++;
-                    }
+                    const unsigned bw = __ballot_sync(0xFFFFFFFFu, (pack[ei] >> decltype(ci)::value) & 1u);
+                    if (lane == 0) hb[(c * M + tid + ei * NT) >> 5] = bw;
                 });
             }
         };
@@ -157,11 +162,11 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
                     if constexpr (kBiased) hard = (int)va < kB;
                     else hard = A::hard_bit(va);
                     [[maybe_unused]] const int van = kBiased ? (2 * kB - 1) - (int)va : 0;
-                    if constexpr (c == CA || c == CP) {
-                        const unsigned bw = __ballot_sync(0xFFFFFFFFu, hard);
-                        if (lane == 0) hb[(c * M + tid + ei * NT) >> 5] = bw;
-                    } else {
-                        pack[ei] = pack[ei] * 2u + (hard ? 1u : 0u);
+                    pack[ei] = pack[ei] * 2u + (hard ? 1u : 0u);
+                    if constexpr (c == CA) hloc[ei] = hard;
+                    if constexpr (c == CP) {
+                        hloc[ei] ^= hard;
+                        hmsg[paddr[PS2][ei] - PS2 * M] = hard ? 1 : 0;
                     }
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
@@ -182,6 +187,7 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
 #pragma unroll
             for (int ei = 0; ei < EPT; ei++) {
                 const int e = tid + ei * NT;
+                bad[ei] = hloc[ei] != (hmsg[e] != 0);            // parity of the three marginals of row-0 check e (:445-447)
                 static_for<0, NROW>([&](auto ri) {
                     constexpr int r = decltype(ri)::value;
                     constexpr int DC = row_degree<P>(r);
@@ -292,7 +298,8 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
                 return synd;
             };
             uint32_t synd = 0;
-            if (tid >= NT - M / 32) synd = syndrome_word(tid - (NT - M / 32));
+#pragma unroll
+            for (int ei = 0; ei < EPT; ei++) synd |= bad[ei] ? 1u : 0u;
             hb_complete = false;
             if (__syncthreads_or(synd != 0) == 0) {
                 flush_pack();
@@ -362,7 +369,7 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
     typedef Proto<RATE> P;
     constexpr int NP = count_p<P>(P::NB);
     const TmParams prm = make_params<RATE>(c);
-    const size_t smem = sizeof(typename MsgStore<T>::type) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32;
+    const size_t smem = sizeof(typename MsgStore<T>::type) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32 + M;   // messages, hard-bit words, hmsg
     auto kern = [] {
         if constexpr (std::is_same<T, double>::value) return &decode_ms_tm_wide_kernel_allregs<RATE, M, T, NT, FRONT>;
         else return &decode_ms_tm_wide_kernel<RATE, M, T, NT, FRONT>;
