@@ -174,7 +174,17 @@ int ctx_for_device_locked(int device, DeviceCtx **out, std::mutex **mu_out) {
 
 }  // namespace
 
+namespace {
+thread_local unsigned long long *t_lane_counter = nullptr;
+}
+void set_lane_counter(unsigned long long *counter) { t_lane_counter = counter; }
+
 WorkCounter::WorkCounter(DeviceCtx &ctx, cudaStream_t stream) : ctx_(ctx), stream_(stream) {
+    if (t_lane_counter) {      // host-pointer path: the lane's stream owns this counter, stream order is all it needs
+        ptr_ = t_lane_counter;
+        err_ = cudaMemsetAsync(ptr_, 0, sizeof(unsigned long long), stream);
+        return;
+    }
     if (!ctx.counters) {
         err_ = cudaMalloc(&ctx.counters, sizeof(unsigned long long) * DeviceCtx::kCounterStride * DeviceCtx::kCounterSlots);
         if (err_ != cudaSuccess) return;
@@ -244,6 +254,7 @@ void runtime_shutdown() {
                 if (lane->buf[i]) cudaFree(lane->buf[i]);
             }
             if (lane->small_host) cudaFreeHost(lane->small_host);
+            if (lane->counters) cudaFree(lane->counters);
         }
         c->lanes.clear();
         c->lanes_free.clear();
@@ -379,6 +390,8 @@ public:
             err_ = cudaStreamCreateWithFlags(&lane->stream[i], cudaStreamNonBlocking);
             if (err_ != cudaSuccess) return;
         }
+        err_ = cudaMalloc(&lane->counters, sizeof(unsigned long long) * 16 * HostLane::kPipe);
+        if (err_ != cudaSuccess) return;
         lane_ = lane.get();
         ctx_.lanes.push_back(std::move(lane));
     }
@@ -400,9 +413,12 @@ private:
 // Launchers touch per-context state (work counters, scratch): they run under the context mutex.  Copies and
 // synchronisation do not, so concurrent callers overlap everything but the launch call itself.
 cudaError_t locked_launch(DeviceCtx &ctx, std::mutex &mu, const BatchLaunchAt &launch, const std::vector<void *> &dptr,
-                          size_t frames, cudaStream_t st, size_t first) {
+                          size_t frames, cudaStream_t st, size_t first, unsigned long long *lane_counter) {
     std::lock_guard<std::mutex> lock(mu);
-    return launch(ctx, dptr, frames, st, first);
+    set_lane_counter(lane_counter);
+    const cudaError_t e = launch(ctx, dptr, frames, st, first);
+    set_lane_counter(nullptr);
+    return e;
 }
 
 int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<HostArray> &arrays, size_t first,
@@ -436,7 +452,7 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
                        arrays[i].bytes_per_frame * count);
         }
         cudaStream_t st = lane.stream[0];
-        cudaError_t e = locked_launch(ctx, mu, launch, dptr, count, st, first);
+        cudaError_t e = locked_launch(ctx, mu, launch, dptr, count, st, first, lane.counters);
         if (e != cudaSuccess) return cuda_error(e, "kernel launch");
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return cuda_error(e, "stream synchronize");
@@ -485,7 +501,7 @@ int run_on_device_host_ptrs(DeviceCtx &ctx, std::mutex &mu, const std::vector<Ho
             }
         }
         if (rc != LDPC_OK) break;
-        cudaError_t e = locked_launch(ctx, mu, launch, dptr, nf, st, f0);
+        cudaError_t e = locked_launch(ctx, mu, launch, dptr, nf, st, f0, lane.counters + 16 * s);
         if (e != cudaSuccess) { rc = cuda_error(e, "kernel launch"); break; }
         for (size_t i = 0; i < arrays.size(); i++) {
             const HostArray &a = arrays[i];

@@ -71,7 +71,13 @@ struct HostLane {
     // small calls (the single-codeword reference API): one pinned, device-mapped staging block
     void *small_host = nullptr;   // host address
     void *small_dev = nullptr;    // the same block as the device sees it
+    // one work counter per stream of the lane: launches on a lane's stream are ordered, so its counter needs neither the
+    // context's ring nor events (class WorkCounter picks it up through set_lane_counter)
+    unsigned long long *counters = nullptr;     // [kPipe][16]
 };
+
+// The calling thread's next launch runs on a lane stream that owns `counter` (nullptr: use the context's ring).
+void set_lane_counter(unsigned long long *counter);
 
 struct DeviceCtx {
     int device = -1;

@@ -44,4 +44,18 @@ for code in range(9):                                                           
     ip = np.zeros_like(want); ip[:, : c.k() // 8] = d
     c.encode_batch(ip)
     assert np.array_equal(ip, want)
+# round 2: i16 on the packed-check-side kernel (all five TM codes it serves), i32 / f64 on the scalar-lane kernel with
+# the in-thread exit test, TM1280 i8 on the packed kernel (covered above), the k = 16384 codes (encode, bf, min-sum)
+for code, ty, eb in ((4, "i16", 2.6), (5, "i16", 1.8), (6, "i16", 3.4), (7, "i16", 2.4), (8, "i16", 1.6), (5, "i32", 1.8), (6, "f64", 3.4), (3, "i16", 3.6)):
+    c = L.LDPCCode(code)
+    _, _, llrs = make_frames(o, code, 20, eb, seed=7, ty=ty)
+    assert same(c.decode_ms_batch(llrs, 30), o.decode_ms_batch(code, llrs, 30, nthreads=4)), (code, ty)
+for code in (9, 10, 11):
+    c = L.LDPCCode(code)
+    d = np.random.default_rng(code).integers(0, 256, (5, c.k() // 8), dtype=np.uint8)
+    cw = c.copy_encode_batch(d)
+    rx = cw.copy(); rx[:, 3] ^= 0x41
+    assert same(c.decode_bf_batch(rx, 10), o.decode_bf_batch(code, rx, 10))
+    llrs = c.hard_to_llrs_batch(rx, "i8")
+    assert same(c.decode_ms_batch(llrs, 6), o.decode_ms_batch(code, llrs, 6, nthreads=4))
 print("sanitize_small OK")
