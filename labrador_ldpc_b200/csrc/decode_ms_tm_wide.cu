@@ -17,6 +17,7 @@
 #include <cstdlib>
 
 #include "biased_arith.cuh"
+#include "bulk_copy.cuh"
 #include "front.cuh"
 #include "llr_arith.cuh"
 #include "runtime.h"
@@ -29,7 +30,13 @@ namespace {
 
 constexpr int kMaxDegW = 18;
 
-template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
+// bytes one frame occupies in the caller's buffer
+template <class T, int FRONT> __host__ __device__ constexpr unsigned wide_frame_bytes(int n) {
+    return FRONT == kFrontSoftF32 ? (unsigned)n * 4u : FRONT == kFrontHard ? (unsigned)n / 8u : (unsigned)n * (unsigned)sizeof(T);
+}
+// STAGE: the next frame's channel values are fetched into shared memory by a bulk asynchronous copy (TMA) while the
+// current frame is decoded, as in decode_ms_tm.cu; chosen by the launcher where two frames fit beside the messages.
+template <int RATE, int M, class T, int NT, int FRONT = kFrontNone, bool STAGE = false>
 __device__ __forceinline__ void
 decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::type *__restrict__ llrs_all,
                          uint8_t *__restrict__ out_all,
@@ -68,7 +75,11 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
     constexpr int PS2 = count_p<P>(2);
     static_assert(P::blk(2).row == 0 && P::blk(2).col == CP && P::blk(2).isp && !P::blk(0).isp && !P::blk(1).isp &&
                   P::blk(0).col == CA && P::blk(1).col == CP && P::blk(3).row == 1, "row 0 must be I(CA) + I(CP) + P(CP)");
-    __shared__ unsigned long long s_frame;
+    constexpr unsigned FB = wide_frame_bytes<T, FRONT>(N);
+    unsigned char *stage = smem_raw + ((sizeof(ST) * NP * M + sizeof(uint32_t) * HBW + M + 15) & ~(size_t)15);   // [2][FB] if STAGE
+    const unsigned char *in_all = reinterpret_cast<const unsigned char *>(llrs_all);
+    __shared__ unsigned long long s_frame[2];
+    __shared__ __align__(8) uint64_t s_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31;
 
@@ -89,13 +100,38 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
         });
     }
 
+    // Frames are claimed one ahead; with STAGE the copy of the next frame is in flight while this one is decoded.
+    const bool use_bulk = STAGE && FB % 16 == 0 && (reinterpret_cast<uintptr_t>(llrs_all) & 15u) == 0;
+    if (tid == 0) {
+        if constexpr (STAGE) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_init_fence();
+        }
+        const unsigned long long f0 = atomicAdd(counter, 1ull);
+        s_frame[0] = f0;
+        if (use_bulk && f0 < batch) bulk_load(stage, in_all + f0 * (unsigned long long)FB, FB, &s_bar[0]);
+    }
+    __syncthreads();
+    unsigned cur = 0, bar_parity = 0;
+
     for (;;) {
-        if (tid == 0) s_frame = atomicAdd(counter, 1ull);
-        __syncthreads();
-        const unsigned long long frame = s_frame;
+        const unsigned long long frame = s_frame[cur];
         if (frame >= batch) break;
-        const typename FrontSrc<FRONT, T>::type *llr =
-            llrs_all + frame * (unsigned long long)(FRONT == kFrontHard ? N / 8 : N);   // front.cuh
+        if (tid == 0) {
+            const unsigned long long fn = atomicAdd(counter, 1ull);
+            s_frame[cur ^ 1] = fn;
+            if (use_bulk && fn < batch)
+                bulk_load(stage + (cur ^ 1) * FB, in_all + fn * (unsigned long long)FB, FB, &s_bar[cur ^ 1]);
+        }
+        const typename FrontSrc<FRONT, T>::type *llr;
+        if (use_bulk) {
+            mbar_wait(&s_bar[cur], (bar_parity >> cur) & 1u);
+            bar_parity ^= 1u << cur;
+            llr = reinterpret_cast<const typename FrontSrc<FRONT, T>::type *>(stage + cur * FB);
+        } else {
+            llr = reinterpret_cast<const typename FrontSrc<FRONT, T>::type *>(in_all + frame * (unsigned long long)FB);
+        }
 
         // zero-initialised state, every call (:368, :374)
         CT Lv[NCOL][EPT], idm[NI > 0 ? NI : 1][EPT], vold[kPackOld ? 1 : NB][EPT];
@@ -335,8 +371,19 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
             if (success) success[frame] = ok ? 1 : 0;
             if (iters_out) iters_out[frame] = iters_run;
         }
-        __syncthreads();
+        __syncthreads();   // hb / msg / stage / s_frame are reused by the next frame
+        cur ^= 1;
     }
+}
+
+// shared memory of one CTA without / with the two staging buffers
+template <int RATE, int M, class T> __host__ __device__ constexpr size_t wide_base_smem() {
+    typedef Proto<RATE> P;
+    return ((sizeof(typename MsgStore<T>::type) * count_p<P>(P::NB) * M + sizeof(uint32_t) * P::NCOL * M / 32 + M + 15) & ~(size_t)15);
+}
+template <int RATE, int M, class T, int FRONT> __host__ __device__ constexpr bool wide_stage() {
+    constexpr size_t fb = wide_frame_bytes<T, FRONT>((Proto<RATE>::NCOL - 1) * M);
+    return fb % 16 == 0 && wide_base_smem<RATE, M, T>() + 2 * fb <= 200 * 1024;
 }
 
 // Two entry points over the same body.  __launch_bounds__(NT) lets ptxas trade registers for occupancy, which is right
@@ -349,8 +396,8 @@ decode_ms_tm_wide_kernel(const TmParams prm, const typename FrontSrc<FRONT, T>::
                          uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
                          uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
                          unsigned long long *__restrict__ counter, const float fscale, const float flimit) {
-    decode_ms_tm_wide_body<RATE, M, T, NT, FRONT>(prm, llrs_all, out_all, batch, max_iters, success, iters_out, counter,
-                                                  fscale, flimit);
+    decode_ms_tm_wide_body<RATE, M, T, NT, FRONT, wide_stage<RATE, M, T, FRONT>()>(prm, llrs_all, out_all, batch, max_iters, success,
+                                                                                    iters_out, counter, fscale, flimit);
 }
 template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
 __global__ void __maxnreg__(65536 / NT > 255 ? 255 : 65536 / NT)
@@ -358,8 +405,8 @@ decode_ms_tm_wide_kernel_allregs(const TmParams prm, const typename FrontSrc<FRO
                                  uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
                                  uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
                                  unsigned long long *__restrict__ counter, const float fscale, const float flimit) {
-    decode_ms_tm_wide_body<RATE, M, T, NT, FRONT>(prm, llrs_all, out_all, batch, max_iters, success, iters_out, counter,
-                                                  fscale, flimit);
+    decode_ms_tm_wide_body<RATE, M, T, NT, FRONT, wide_stage<RATE, M, T, FRONT>()>(prm, llrs_all, out_all, batch, max_iters, success,
+                                                                                    iters_out, counter, fscale, flimit);
 }
 
 template <int RATE, int M, class T, int NT, int FRONT = kFrontNone>
@@ -369,7 +416,9 @@ cudaError_t launch_wide(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uin
     typedef Proto<RATE> P;
     constexpr int NP = count_p<P>(P::NB);
     const TmParams prm = make_params<RATE>(c);
-    const size_t smem = sizeof(typename MsgStore<T>::type) * NP * M + sizeof(uint32_t) * P::NCOL * M / 32 + M;   // messages, hard-bit words, hmsg
+    // messages, hard-bit words, hmsg (+ two frames of staging where they fit)
+    const size_t smem = wide_base_smem<RATE, M, T>() +
+                        (wide_stage<RATE, M, T, FRONT>() ? 2 * (size_t)wide_frame_bytes<T, FRONT>((P::NCOL - 1) * M) : 0);
     auto kern = [] {
         if constexpr (std::is_same<T, double>::value) return &decode_ms_tm_wide_kernel_allregs<RATE, M, T, NT, FRONT>;
         else return &decode_ms_tm_wide_kernel<RATE, M, T, NT, FRONT>;

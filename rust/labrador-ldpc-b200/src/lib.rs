@@ -16,6 +16,9 @@ pub enum LDPCCode {
     TC128 = 0, TC256 = 1, TC512 = 2,
     TM1280 = 3, TM1536 = 4, TM2048 = 5,
     TM5120 = 6, TM6144 = 7, TM8192 = 8,
+    /// Extension: the k = 16384 codes whose parity-check constants the reference carries without supporting them
+    /// (src/lib.rs:81-83).  Decoded like every TM code, encoded through the sparse parity-check matrix.
+    TM20480 = 9, TM24576 = 10, TM32768 = 11,
 }
 
 #[derive(Debug)]

@@ -25,12 +25,14 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps * 1e-3
 
 
-def cpu_ns(fn, min_s=0.3):
+def cpu_ns(fn, per_call, min_s=0.3):
+    """ns per codeword of `fn`, which processes `per_call` copies of the vector on ONE thread (the ctypes / numpy
+    overhead of a call is amortised over the copies, as a Rust bench loop has none)."""
     fn()
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < min_s:
         fn(); n += 1
-    return (time.perf_counter() - t0) / n * 1e9
+    return (time.perf_counter() - t0) / (n * per_call) * 1e9
 
 
 def main():
@@ -54,7 +56,9 @@ def main():
         assert bool(okbf.all()) and torch.equal(obf[0, : n // 8].cpu(), torch.from_numpy(cw))
         res["bf"] = timeit(lambda: c.decode_bf_batch(d_rx, 50, output=obf, success=okbf, iters=itbf)) / B * 1e9
         wok, wit, _ = o.decode_bf(code, rx, 50); assert wok and wit == int(itbf[0])
-        res["bf_cpu"] = cpu_ns(lambda: o.decode_bf(code, rx, 50))
+        R = max(4, 65536 // n)                       # copies per CPU call
+        rxR = np.tile(rx, (R, 1))
+        res["bf_cpu"] = cpu_ns(lambda: o.decode_bf_batch(code, rxR, 50, nthreads=1), R)
         iters = [int(itbf[0])]
         for ty in ("i8", "f32"):
             llr = c.hard_to_llrs_batch(d_rx, ty)
@@ -63,7 +67,8 @@ def main():
             res[ty] = timeit(lambda: c.decode_ms_batch(llr, 50, output=om, success=okm, iters=itm)) / B * 1e9
             l1 = llr[0].cpu().numpy()
             wok, wit, _ = o.decode_ms(code, l1, 50); assert wok and wit == int(itm[0])
-            res[ty + "_cpu"] = cpu_ns(lambda: o.decode_ms(code, l1, 50))
+            lR = np.tile(l1, (R, 1))
+            res[ty + "_cpu"] = cpu_ns(lambda: o.decode_ms_batch(code, lR, 50, nthreads=1), R)
             iters.append(int(itm[0]))
             del llr, om
         EB = max(B, min(1 << 24, (1 << 31) // n))
@@ -71,7 +76,8 @@ def main():
         d_cw = torch.empty((EB, n // 8), dtype=torch.uint8, device="cuda")
         t_enc = timeit(lambda: c.copy_encode_batch(d_data, d_cw))
         assert torch.equal(d_cw[EB - 1].cpu(), torch.from_numpy(cw))
-        enc_cpu = cpu_ns(lambda: o.copy_encode(code, data))
+        dR = np.tile(data, (R, 1))
+        enc_cpu = cpu_ns(lambda: o.copy_encode_batch(code, dR, nthreads=1), R)
         out.append("| %s | %d | %.2f | %.0f | %.2f | %.0f | %.2f | %.0f | %d / %d / %d | %.0f | %.1f |" % (
             c.name, B, res["bf"], res["bf_cpu"], res["i8"], res["i8_cpu"], res["f32"], res["f32_cpu"], iters[0], iters[1], iters[2],
             EB * (k // 8) / t_enc / 1e6, (k // 8) / enc_cpu * 1e3))
