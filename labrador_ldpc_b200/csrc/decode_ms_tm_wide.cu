@@ -383,7 +383,15 @@ template <int RATE, int M, class T> __host__ __device__ constexpr size_t wide_ba
 }
 template <int RATE, int M, class T, int FRONT> __host__ __device__ constexpr bool wide_stage() {
     constexpr size_t fb = wide_frame_bytes<T, FRONT>((Proto<RATE>::NCOL - 1) * M);
-    return fb % 16 == 0 && wide_base_smem<RATE, M, T>() + 2 * fb <= 200 * 1024;
+    // Measured on every code (profiles/raw/r02j_wide_staging_log.txt against r02h_wide_kernel_log.txt): +1.5 % on TM2048
+    // (f32, i32: the C2 configuration), -1 ... -5.5 % elsewhere (the kernels are ALU-pipe bound, the staging buffers
+    // cost residency or L1), so it is enabled where it pays.  LDPC_WIDE_STAGE_ALL (compile time) stages wherever it fits.
+#ifdef LDPC_WIDE_STAGE_ALL
+    constexpr bool wanted = true;
+#else
+    constexpr bool wanted = RATE == 0 && M == 512;
+#endif
+    return wanted && fb % 16 == 0 && wide_base_smem<RATE, M, T>() + 2 * fb <= 200 * 1024;
 }
 
 // Two entry points over the same body.  __launch_bounds__(NT) lets ptxas trade registers for occupancy, which is right
