@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "liblabrador_ldpc.so")
 
-SOURCES = ["code_tables.cpp", "runtime.cu", "capi.cu", "decode_ms_generic.cu", "decode_ms_tm.cu", "decode_ms_tm_i16.cu", "decode_ms_tm_wide.cu", "decode_ms_tc.cu", "decode_ms_tc_x2.cu", "decode_bf.cu", "decode_bf_tm.cu", "decode_bf_tc.cu",
+SOURCES = ["code_tables.cpp", "runtime.cu", "capi.cu", "decode_ms_generic.cu", "decode_ms_tm.cu", "decode_ms_tm_i16.cu", "decode_ms_tm_cluster.cu", "decode_ms_tm_wide.cu", "decode_ms_tc.cu", "decode_ms_tc_x2.cu", "decode_bf.cu", "decode_bf_tm.cu", "decode_bf_tc.cu",
            "encode.cu", "encode_tm.cu", "convert.cu", "channel.cu"]
 
 NVCC_FLAGS = [

@@ -1,7 +1,7 @@
 // Specialised min-sum decoder for the TM codes with i16 LLRs: 32-bit variable side, packed 16-bit check side.
 //
 // Replaces LDPCCode::decode_ms::<i16> (reference src/decoder.rs:347-475; DecodeFrom for i16, :52-58) for
-// TM1536 ... TM8192; results (decoded bytes, success flag, iteration count) are bit-identical to the reference's.
+// TM1280 ... TM8192; results (decoded bytes, success flag, iteration count) are bit-identical to the reference's.
 //
 // Same skeleton as the packed i8 kernel (decode_ms_tm.cu: lane pairs (x, x + S) inside every quarter of a block, thread t
 // owns word slot t of every prototype column and row, identity-block messages in registers, pi_k-block messages in
@@ -436,7 +436,7 @@ cudaError_t launch_i16_front(DeviceCtx &ctx, const CodeInfo &c, const void *llrs
 // LABRADOR_LDPC_TM_I16_WIDE=1 keeps i16 on the scalar-lane kernel (A/B runs and tests).
 bool has_decode_ms_tm_i16(int code) {
     static const bool off = [] { const char *e = getenv("LABRADOR_LDPC_TM_I16_WIDE"); return e && atoi(e) != 0; }();
-    return !off && code >= 4 && code <= 8;
+    return !off && code >= 3 && code <= 8;
 }
 
 // Returns true (and launches) if the packed-check-side kernel covers (code, i16, front).
@@ -445,6 +445,10 @@ bool launch_decode_ms_tm_i16(DeviceCtx &ctx, int code, const void *llrs, uint8_t
     if (!has_decode_ms_tm_i16(code) || front.kind == kFrontHard) return false;
     const CodeInfo &c = *code_info(code);
     switch (code) {
+        case 3:      // TM1280: M = 128, 64 threads per codeword, compiled for six resident CTAs per SM like the i8 kernel
+            if (!structure_matches<2>(c) || c.m != 128) return false;
+            *err = launch_i16_front<2, 128, 1, 6>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+            return true;
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
             *err = launch_i16_front<1, 256, 1, 1>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);

@@ -29,6 +29,10 @@ bool has_decode_ms_tm_i8(int code);
 bool launch_decode_ms_tm_i16(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch, size_t max_iters,
                              uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err, const Front &front);
 bool has_decode_ms_tm_i16(int code);
+// decode_ms_tm_cluster.cu: i8 on the k = 16384 codes, one codeword per cluster of four CTAs
+bool launch_decode_ms_tm_cluster(DeviceCtx &ctx, int code, const void *llrs, uint8_t *output, size_t batch, size_t max_iters,
+                                 uint8_t *success, uint32_t *iters, cudaStream_t stream, cudaError_t *err, const Front &front);
+bool has_decode_ms_tm_cluster(int code);
 bool launch_decode_ms_tm_wide(DeviceCtx &ctx, int code, int llr_type, const void *llrs, uint8_t *output, size_t batch,
                               size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream,
                               cudaError_t *err, const Front &front);
@@ -315,6 +319,8 @@ cudaError_t launch_decode_ms(DeviceCtx &ctx, int code, int llr_type, const void 
         cudaError_t err = cudaSuccess;
         if (launch_decode_ms_tm_i8(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err, front))
             return err;
+        if (launch_decode_ms_tm_cluster(ctx, code, llrs, output, batch, max_iters, success, iters, stream, &err, front))
+            return err;
     }
     if (!force_generic()) {
         cudaError_t err = cudaSuccess;
@@ -342,6 +348,7 @@ bool front_supported(int kind, int llr_type) {
 
 const char *decode_ms_kernel_name(int code, int llr_type) {
     if (llr_type == kI8 && has_decode_ms_tm_i8(code) && !force_generic()) return "ms_tm_s16x2<i8>";
+    if (llr_type == kI8 && has_decode_ms_tm_cluster(code) && !force_generic()) return "ms_tm_cluster<i8>";
     if (llr_type == kI16 && has_decode_ms_tm_i16(code) && !force_generic()) return "ms_tm_s16x2<i16>";
     if (has_decode_ms_tm_wide(code, llr_type) && !force_generic()) {
         static const char *wide[kNumLlrTypes] = {"ms_tm_wide<i8>", "ms_tm_wide<i16>", "ms_tm_wide<i32>", "ms_tm_wide<f32>", "ms_tm_wide<f64>"};

@@ -138,3 +138,35 @@ def test_converters_and_reference_signature_calls(ldpc, oracle):
     ok, it = c.decode_ms(llr1, out, maxiters=10)
     wok, wit, wout = oracle.decode_ms(code, llr1, 10)
     assert (ok, it) == (wok, wit) and np.array_equal(out, wout)
+
+
+@pytest.mark.parametrize("code", list(CODES))
+def test_cluster_kernel_larger_batch_and_unaligned_buffers(ldpc, oracle, code):
+    """More frames than resident clusters (every cluster decodes several frames: staging double buffer, state
+    re-initialisation, static frame assignment), tight iteration caps, and a misaligned LLR buffer (plain-load path)."""
+    import torch
+    c = ldpc.LDPCCode(code)
+    cw, llrs = frames(ldpc, code, 150, EBN0[code] + 0.3, seed=800 + code, ty="i8")
+    for maxiters in (100, 7, 1):
+        want = oracle.decode_ms_batch(code, llrs, maxiters, nthreads=16)
+        got = c.decode_ms_batch(llrs, maxiters)
+        assert_exact(got, want, "%s cluster kernel maxiters=%d" % (CODES[code], maxiters))
+    raw = torch.zeros(llrs.size + 64, dtype=torch.int8, device="cuda")
+    for off in (1, 8):
+        view = raw[off:off + llrs.size].view(llrs.shape)
+        view.copy_(torch.from_numpy(llrs))
+        got = c.decode_ms_batch(view, 30)
+        torch.cuda.synchronize()
+        assert_exact([g.cpu().numpy() for g in got], oracle.decode_ms_batch(code, llrs, 30, nthreads=16),
+                     "%s cluster kernel, LLRs at byte offset %d" % (CODES[code], off))
+    # the table-driven kernel (the path of the other LLR types) gives the same answer
+    import os, subprocess, sys, tempfile
+    env = dict(os.environ, LABRADOR_LDPC_TM_CLUSTER="0", LABRADOR_LDPC_NO_REBUILD="1")
+    script = ("import sys, numpy as np; sys.path.insert(0, %r); import labrador_ldpc_b200 as L; "
+              "x = np.load(sys.argv[1]); out, ok, it = L.LDPCCode(%d).decode_ms_batch(x, 30); "
+              "np.savez(sys.argv[2], out=out, ok=ok, it=it)" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), code))
+    with tempfile.TemporaryDirectory() as d:
+        np.save(d + "/x.npy", llrs[:40])
+        subprocess.check_call([sys.executable, "-c", script, d + "/x.npy", d + "/o.npz"], env=env)
+        z = np.load(d + "/o.npz")
+        assert_exact((z["out"], z["ok"], z["it"]), oracle.decode_ms_batch(code, llrs[:40], 30, nthreads=16), CODES[code] + " table-driven")

@@ -694,12 +694,13 @@ def test_specialised_kernel_dispatch(ldpc):
             assert name == ("ms_tc_x2<i8>" if ty == "i8" else "ms_tc_warp<%s>" % ty)
         elif ty == "i8":
             assert name == "ms_tm_s16x2<i8>"                # TM1280 too since round 2 (M = 128 on the packed kernel)
-        elif ty == "i16" and code >= 4:
+        elif ty == "i16":
             assert name == "ms_tm_s16x2<i16>"               # packed 16-bit check side (decode_ms_tm_i16.cu)
         else:
             assert name == "ms_tm_wide<%s>" % ty
-    for code in (9, 10, 11):                                 # the k = 16384 codes: table-driven kernel
-        assert ldpc.LDPCCode(code).decode_ms_kernel_name("i8") == "ms_generic<i8>"
+    for code in (9, 10, 11):                                 # the k = 16384 codes: one codeword per cluster of four CTAs (i8)
+        assert ldpc.LDPCCode(code).decode_ms_kernel_name("i8") == "ms_tm_cluster<i8>"
+        assert ldpc.LDPCCode(code).decode_ms_kernel_name("f32") == "ms_generic<f32>"
 
 
 def test_mixed_code_batch_on_concurrent_streams(ldpc, oracle):
