@@ -10,9 +10,13 @@
 // naturally four ways: CTA r of the cluster owns quarter r of every prototype column AND of every prototype row
 // (M/8 word slots, each two 16-bit lanes: elements x and x + M/8 of the quarter).  Then
 //   * identity blocks connect a check and a variable of the same thread (registers), as before;
-//   * a permutation block connects variable quarter r with check quarter (r - theta) mod 4: its messages live in the
-//     shared memory of the CTA that owns the CHECKS, in check order, and the variable side reads / writes them through
-//     DISTRIBUTED SHARED MEMORY (mapa + ld / st.shared::cluster) -- the address of every block is a per-thread constant;
+//   * a permutation block connects variable quarter r with check quarter (r - theta) mod 4.  Its messages cross the
+//     cluster through DISTRIBUTED SHARED MEMORY, and always as a PUSH: the variable side stores v into a buffer of the CTA
+//     that owns the checks (check order), the check side stores u into a buffer of the CTA that owns the variables
+//     (variable order), both with st.shared::cluster to a per-thread constant address (mapa); every load is local.
+//     Distributed shared memory moves ~20 bytes per clock per SM at ~215 cycles latency (B300_MICROARCH.md): pulled at
+//     the start of a phase that is 2500 exposed cycles per iteration (the first version of this kernel, 0.37 M cw/s on
+//     TM32768); pushed as soon as produced, the transfer drains behind the rest of the phase's arithmetic;
 //   * the two barriers of an iteration become cluster barriers (barrier.cluster arrive.release / wait.acquire, which
 //     also order the remote stores), and the exit decision is an OR over the four CTAs (one flag word per CTA, written
 //     into every CTA's shared memory before the barrier that the next phase needs anyway).
@@ -125,8 +129,10 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
                   "row 0 must be I(CA) + I(CP) + P(CP)");
 
     extern __shared__ __align__(16) uint32_t smem_cl[];
-    uint32_t *msg = smem_cl;                         // [NP][S] messages of this CTA's CHECK quarter, check order
-    uint32_t *hb = msg + NP * S;                     // [NCOL][QW] packed hard decisions of this CTA's variable quarter
+    uint32_t *msg = smem_cl;                         // [NP][S] v messages of this CTA's CHECK quarter, check order (pushed by the variable side)
+    uint32_t *ubuf = msg + NP * S;                   // [NP][S] u messages of this CTA's VARIABLE quarter, variable order (pushed by the check side)
+    uint2 *tab = reinterpret_cast<uint2 *>(ubuf + NP * S);   // [NP][WPT][NT] check side: {shared::cluster address in ubuf, lane swap}
+    uint32_t *hb = reinterpret_cast<uint32_t *>(tab + NP * WPT * NT);   // [NCOL][QW] packed hard decisions of this CTA's variable quarter
     constexpr unsigned FBL = (NCOL - 1) * Q;         // staged bytes per frame: this quarter of every data column
     unsigned char *stage = reinterpret_cast<unsigned char *>(hb + ((HBL + 3) & ~3));   // [2][FBL]
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -134,7 +140,7 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t rank = cl_rank();                 // = the quarter this CTA owns
-    const uint32_t msg_sa = smem_addr(msg), hb_sa = smem_addr(hb), flag_sa = smem_addr(s_flag);
+    const uint32_t msg_sa = smem_addr(msg), ubuf_sa = smem_addr(ubuf), hb_sa = smem_addr(hb), flag_sa = smem_addr(s_flag);
 
     // per-thread constants: shared::cluster address + lane swap of every permutation block (variable side)
     uint32_t paddr[NP > 0 ? NP : 1][WPT], pswp[NP > 0 ? NP : 1][WPT];
@@ -152,6 +158,13 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
                 const int w = (wv - phi_lo) & (S - 1);
                 paddr[ps][wi] = cl_map(msg_sa + (uint32_t)(ps * S + w) * 4u, (uint32_t)q);
                 pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 16u : 0u;
+                // the same block seen from the check this thread owns (quarter `rank`, slot wv): the variable pair it talks to
+                const int qv2 = ((int)prm.theta[b] + (int)rank) & 3;
+                const int phi2 = prm.phi[b][rank];
+                const int t2 = wv + phi2 % S;                                 // carry out of the half quarter <=> the var side's borrow
+                const int wv2 = t2 & (S - 1);
+                tab[(ps * WPT + wi) * NT + tid] = make_uint2(cl_map(ubuf_sa + (uint32_t)(ps * S + wv2) * 4u, (uint32_t)qv2),
+                                                             (((phi2 / S) ^ (t2 >= S ? 1 : 0)) & 1) ? 16u : 0u);
             }
         });
     }
@@ -209,10 +222,10 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
 #pragma unroll
             for (int b = 0; b < NB; b++) cc[b][wi] = 0x007f007fu;
 #pragma unroll
-            for (int p = 0; p < NP; p++) msg[p * S + wv] = 0;
+            for (int p = 0; p < NP; p++) ubuf[p * S + wv] = 0;          // u = 0 before the first iteration; v is written before it is read
         }
         for (int i = tid; i < HBL; i += NT) hb[i] = 0;
-        cl_sync();                       // every CTA's messages are zero before anyone reads them remotely
+        cl_sync();                       // every CTA has re-initialised its buffers before anyone pushes into them
 
         unsigned iters_run = max_iters;
         bool ok = false, hb_complete = true;
@@ -257,7 +270,7 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
                             uint32_t u;
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
-                                u = lrot(cl_ld(paddr[ps][wi]), pswp[ps][wi]);
+                                u = ubuf[ps * S + tid + wi * NT];            // pushed here, in this thread's lane order, by the check side
                             } else {
                                 u = idm[count_i<P>(b)][wi];
                             }
@@ -325,8 +338,12 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
                             constexpr int k = pos_in_row<P>(b);
                             const uint32_t nm = sign7_mask(sx ^ ck[k]);
                             const uint32_t u = __vadd2(mu[k], nm) ^ nm;                    // +-mu, two's complement
-                            if constexpr (P::blk(b).isp) msg[count_p<P>(b) * S + wv] = u;
-                            else idm[count_i<P>(b)][wi] = u;
+                            if constexpr (P::blk(b).isp) {
+                                const uint2 t = tab[(count_p<P>(b) * WPT + wi) * NT + tid];
+                                cl_st(t.x, lrot(u, t.y));                                  // push to the CTA that owns the variables
+                            } else {
+                                idm[count_i<P>(b)][wi] = u;
+                            }
                         }
                     });
                 });
@@ -336,7 +353,7 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
 #pragma unroll
             for (int wi = 0; wi < WPT; wi++) synd |= bad[wi];
             hb_complete = false;
-            if (!cluster_or(synd != 0)) {       // (its barrier also publishes this phase's u to the other CTAs)
+            if (!cluster_or(synd != 0)) {       // (its barrier also publishes the u pushed in this phase)
                 flush_pack();
                 hb_complete = true;
                 cl_sync();                      // every quarter's hard bits are in place
@@ -403,7 +420,8 @@ cudaError_t launch_cluster(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, 
     constexpr int NP = count_p<P>(P::NB);
     constexpr int Q = M / 4, S = Q / 2, NT = S / WPT;
     const TmParams prm = make_params<RATE>(c);
-    const size_t smem = ((size_t)NP * S + (((size_t)P::NCOL * Q / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) +
+    // v buffer, u buffer, check-side address table, hard-bit words, two staging buffers
+    const size_t smem = ((size_t)2 * NP * S + (size_t)2 * NP * S + (((size_t)P::NCOL * Q / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) +
                         2 * (size_t)(P::NCOL - 1) * Q;
     auto kern = decode_ms_tm_cluster_kernel<RATE, M, WPT, MINB>;
     static bool configured[kMaxDevices] = {};
