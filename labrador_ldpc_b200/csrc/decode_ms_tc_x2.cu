@@ -13,6 +13,7 @@
 // alone (masked re-initialisation) while the other half carries on -- iteration counts stay exact and a
 // slow codeword costs its partner nothing.  Hard decisions of the two codewords share a byte (bits 0 / 1),
 // so one XOR chain yields both parities of a check (:445-447).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -55,7 +56,36 @@ __device__ __forceinline__ void min_excluding_self8(const uint32_t (&a)[8], uint
     mu[7] = __vminu2(p3, a[6]);
 }
 
-template <int M, int FRONT>
+// The same on fp16 lanes (as ARITH 6 of decode_ms_tm.cu): a lane holding the signed integer d (|d| < 1024) as the fp16
+// subnormal d * 2^-24; |.| is a free operand modifier of HMNMX2 / VHMNMX, so d = C - 127 (one HADD2 on the FMA pipe) replaces
+// the VABSDIFF4 on the ALU pipe, and the results are bit-identical to the integer |d|.
+__device__ __forceinline__ uint32_t x2_hmin2a(uint32_t x, uint32_t y) {
+    __half2 r = __hmin2(__habs2(*reinterpret_cast<__half2 *>(&x)), __habs2(*reinterpret_cast<__half2 *>(&y)));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ uint32_t x2_hmin3a(uint32_t x, uint32_t y, uint32_t z) {
+    __half2 r = __hmin2(__hmin2(__habs2(*reinterpret_cast<__half2 *>(&x)), __habs2(*reinterpret_cast<__half2 *>(&y))),
+                        __habs2(*reinterpret_cast<__half2 *>(&z)));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+__device__ __forceinline__ void min_excluding_self8_h(const uint32_t (&a)[8], uint32_t (&mu)[8]) {
+    const uint32_t s3 = x2_hmin2a(a[6], a[7]);
+    const uint32_t s2 = x2_hmin3a(a[4], a[5], s3);
+    const uint32_t s1 = x2_hmin3a(a[2], a[3], s2);
+    mu[0] = x2_hmin2a(a[1], s1);
+    mu[1] = x2_hmin2a(a[0], s1);
+    const uint32_t p1 = x2_hmin2a(a[0], a[1]);
+    mu[2] = x2_hmin3a(p1, a[3], s2);
+    mu[3] = x2_hmin3a(p1, a[2], s2);
+    const uint32_t p2 = x2_hmin3a(p1, a[2], a[3]);
+    mu[4] = x2_hmin3a(p2, a[5], s3);
+    mu[5] = x2_hmin3a(p2, a[4], s3);
+    const uint32_t p3 = x2_hmin3a(p2, a[4], a[5]);
+    mu[6] = x2_hmin2a(p3, a[7]);
+    mu[7] = x2_hmin2a(p3, a[6]);
+}
+
+template <int M, int FRONT, bool HABS>
 __global__ void __launch_bounds__(32 * kX2Warps)
 decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
                          uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
@@ -176,12 +206,18 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     const uint32_t cor = (cv & ~km) | (0x007f007fu & km);           // killed -> v = 0
                     vold[b][ei] = cor;
                     ck[k] = cor;
-                    a[k] = __vabsdiffu4(cor, 0x007f007fu);                          // |v|
+                    if constexpr (HABS) {
+                        const __half2 d = __hsub2(*reinterpret_cast<const __half2 *>(&cor), __half2(__ushort_as_half(0x007f), __ushort_as_half(0x007f)));
+                        a[k] = *reinterpret_cast<const uint32_t *>(&d);             // -v as a signed fp16 lane
+                    } else {
+                        a[k] = __vabsdiffu4(cor, 0x007f007fu);                      // |v|
+                    }
                     sx ^= cor;                                                      // bit 7: product of signs
                     par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];
                 });
                 par_any |= par;
-                min_excluding_self8(a, mu);
+                if constexpr (HABS) min_excluding_self8_h(a, mu);
+                else min_excluding_self8(a, mu);
                 tc_static_for<0, 8>([&](auto ki) {
                     constexpr int k = decltype(ki)::value;
                     constexpr int b = r * 8 + k;
@@ -222,13 +258,13 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
     }
 }
 
-template <int M, int FRONT>
-cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+template <int M, int FRONT, bool HABS>
+cudaError_t launch_x2h(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, const Front &front) {
     constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
     const size_t warp_bytes = ((4u * CWW * x2_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kX2Warps;
-    auto kern = decode_ms_tc_i8x2_kernel<M, FRONT>;
+    auto kern = decode_ms_tc_i8x2_kernel<M, FRONT, HABS>;
     static bool configured[kMaxDevices] = {};
     static int per_sm_cached[kMaxDevices] = {};
     if (!configured[ctx.device]) {
@@ -253,6 +289,15 @@ cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
         success, iters, counter, front.scale, front.limit);
     count_launch();
     return cudaGetLastError();
+}
+
+// LABRADOR_LDPC_TC_X2_HABS=0 keeps |v| and the minima on integer lanes (VABSDIFF4 + VIMNMX): A/B runs and tests.
+template <int M, int FRONT>
+cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+                      size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, const Front &front) {
+    static const bool habs = [] { const char *e = getenv("LABRADOR_LDPC_TC_X2_HABS"); return !e || atoi(e) != 0; }();
+    if (habs) return launch_x2h<M, FRONT, true>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+    return launch_x2h<M, FRONT, false>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
 }
 
 template <int M>
