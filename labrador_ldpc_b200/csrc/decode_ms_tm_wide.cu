@@ -289,20 +289,56 @@ decode_ms_tm_wide_body(const TmParams &prm, const typename FrontSrc<FRONT, T>::t
                         }
                     });
                     // min over the other edges = (|v| == min1 ? min2 : min1)  (:391-395)
-                    suf[DC - 1] = a[DC - 1];
+                    // f32 / i32 have a three-input minimum (FMNMX3 / VIMNMX3 on sm_100a, which nested two-input minima
+                    // compile to): prefixes and suffixes at pair boundaries, 2 DC - 2 minima instead of 3 DC - 6; f64 has
+                    // no minimum instruction at all and keeps the form with the fewest two-input minima
+                    constexpr bool kMin3 = std::is_same<T, float>::value || std::is_same<T, int32_t>::value;
+                    CT muv[kMaxDegW];
+                    if constexpr (kMin3 && DC >= 4) {
+                        constexpr int NPAIR = DC / 2;
+                        constexpr bool ODD = (DC & 1) != 0;
+                        if constexpr (ODD) suf[NPAIR] = a[DC - 1];
 #pragma unroll
-                    for (int k = DC - 2; k >= 1; k--) suf[k] = A::min(a[k], suf[k + 1]);
-                    CT pre = a[0];
+                        for (int j = NPAIR - 1; j >= 1; j--) {
+                            if (j == NPAIR - 1 && !ODD) suf[j] = A::min(a[2 * j], a[2 * j + 1]);
+                            else suf[j] = A::min(A::min(a[2 * j], a[2 * j + 1]), suf[j + 1]);
+                        }
+                        CT pre2 = A::zero();
+#pragma unroll
+                        for (int j = 0; j < NPAIR; j++) {
+                            const bool has_pre = j > 0, has_suf = (j + 1 < NPAIR) || ODD;
+                            if (has_pre && has_suf) {
+                                muv[2 * j] = A::min(A::min(pre2, a[2 * j + 1]), suf[j + 1]);
+                                muv[2 * j + 1] = A::min(A::min(pre2, a[2 * j]), suf[j + 1]);
+                            } else if (has_suf) {
+                                muv[2 * j] = A::min(a[2 * j + 1], suf[j + 1]);
+                                muv[2 * j + 1] = A::min(a[2 * j], suf[j + 1]);
+                            } else {
+                                muv[2 * j] = A::min(pre2, a[2 * j + 1]);
+                                muv[2 * j + 1] = A::min(pre2, a[2 * j]);
+                            }
+                            if (j + 1 < NPAIR || ODD)
+                                pre2 = has_pre ? A::min(A::min(pre2, a[2 * j]), a[2 * j + 1]) : A::min(a[2 * j], a[2 * j + 1]);
+                        }
+                        if constexpr (ODD) muv[DC - 1] = pre2;
+                    } else {
+                        suf[DC - 1] = a[DC - 1];
+#pragma unroll
+                        for (int k = DC - 2; k >= 1; k--) suf[k] = A::min(a[k], suf[k + 1]);
+                        CT pre = a[0];
+#pragma unroll
+                        for (int k = 0; k < DC; k++) {
+                            if (k == 0) muv[k] = suf[1];
+                            else if (k == DC - 1) muv[k] = pre;
+                            else muv[k] = A::min(pre, suf[k + 1]);
+                            if (k > 0 && k < DC - 1) pre = A::min(pre, a[k]);
+                        }
+                    }
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).row == r) {
                             constexpr int k = pos_in_row<P>(b);
-                            CT mu;
-                            if constexpr (k == 0) mu = suf[1];
-                            else if constexpr (k == DC - 1) mu = pre;
-                            else mu = A::min(pre, suf[k + 1]);
-                            if constexpr (k > 0 && k < DC - 1) pre = A::min(pre, a[k]);
-                            CT u = mu;
+                            CT u = muv[k];
                             if (stot != sg[k]) u = A::neg(u);                          // :398-405
                             if constexpr (P::blk(b).isp) msg[count_p<P>(b) * M + e] = (ST)u;
                             else idm[count_i<P>(b)][ei] = u;
