@@ -113,7 +113,8 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(M / 8 / WPT, MINB)
 decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
                             unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                             uint32_t *__restrict__ iters_out,
-                            const uint32_t one /* == 1: keeps carry-free packing and subtractions on the FMA pipe (IMAD) */) {
+                            const uint32_t one /* == 1: keeps carry-free packing and subtractions on the FMA pipe (IMAD) */,
+                            const uint32_t remote /* all ones; 0 (timing experiments only, results wrong): every push stays in the own CTA */) {
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
     constexpr int NP = count_p<P>(NB), NI = NB - NP;
@@ -156,14 +157,14 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
                 const int phi_lo = phi % S, phi_hi = phi / S;
                 const int borrow = wv < phi_lo ? 1 : 0;
                 const int w = (wv - phi_lo) & (S - 1);
-                paddr[ps][wi] = cl_map(msg_sa + (uint32_t)(ps * S + w) * 4u, (uint32_t)q);
+                paddr[ps][wi] = cl_map(msg_sa + (uint32_t)(ps * S + w) * 4u, ((uint32_t)q & remote) | (rank & ~remote));
                 pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 16u : 0u;
                 // the same block seen from the check this thread owns (quarter `rank`, slot wv): the variable pair it talks to
                 const int qv2 = ((int)prm.theta[b] + (int)rank) & 3;
                 const int phi2 = prm.phi[b][rank];
                 const int t2 = wv + phi2 % S;                                 // carry out of the half quarter <=> the var side's borrow
                 const int wv2 = t2 & (S - 1);
-                tab[(ps * WPT + wi) * NT + tid] = make_uint2(cl_map(ubuf_sa + (uint32_t)(ps * S + wv2) * 4u, (uint32_t)qv2),
+                tab[(ps * WPT + wi) * NT + tid] = make_uint2(cl_map(ubuf_sa + (uint32_t)(ps * S + wv2) * 4u, ((uint32_t)qv2 & remote) | (rank & ~remote)),
                                                              (((phi2 / S) ^ (t2 >= S ? 1 : 0)) & 1) ? 16u : 0u);
             }
         });
@@ -446,8 +447,10 @@ cudaError_t launch_cluster(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, 
     unsigned long long clusters = (unsigned long long)clusters_cached[ctx.device];
     if (clusters > batch) clusters = batch;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
+    // LABRADOR_LDPC_CLUSTER_LOCAL_PUSH=1: timing experiment (profiles/r02_cluster.md), decodes garbage
+    static const uint32_t remote = [] { const char *e = getenv("LABRADOR_LDPC_CLUSTER_LOCAL_PUSH"); return (e && atoi(e) != 0) ? 0u : 0xFFFFFFFFu; }();
     kern<<<(unsigned)(clusters * kCL), NT, smem, stream>>>(prm, static_cast<const int8_t *>(llrs), output,
-                                                            (unsigned long long)batch, mi, success, iters, 1u);
+                                                            (unsigned long long)batch, mi, success, iters, 1u, remote);
     count_launch();
     return cudaGetLastError();
 }
