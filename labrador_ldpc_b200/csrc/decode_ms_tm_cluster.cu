@@ -498,7 +498,7 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
 // of a block are packed to their low bytes (one PRMT), rotated (one SHF) and stored once; the receiver unpacks with one
 // PRMT per word (zero fill for v, sign fill for u).  Half the stores, half the bytes, the same arithmetic.
 // Block 2 (row 0's permutation block) keeps the pair form for v: its high bytes carry the marginals of the exit test.
-template <int RATE, int M, int MINB>
+template <int RATE, int M, int MINB, bool ASYNC>
 __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(M / 16, MINB)
 decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
                              unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
@@ -527,11 +527,17 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
     unsigned char *stage = reinterpret_cast<unsigned char *>(hb + ((HBL + 3) & ~3));   // [2][FBL]
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_flag[kCL];
+    // ASYNC (see the pair kernel): [0] counts the bytes of v pushed into msg2 / msg4, [1] the bytes of u plus the four row-0 flags
+    __shared__ __align__(8) uint64_t s_abar[2];
+    __shared__ uint32_t s_vbar[NP], s_ubar[NP];
+    __shared__ uint32_t s_aflag[2][kCL];
+    constexpr uint32_t kVBytes = (uint32_t)(S + (NP - 1) * NT) * 4u, kUBytes = (uint32_t)NP * NT * 4u + 4u * kCL;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t rank = cl_rank();
     const uint32_t msg2_sa = smem_addr(msg2), msg4_sa = smem_addr(msg4), ubuf_sa = smem_addr(ubuf), hb_sa = smem_addr(hb),
                    flag_sa = smem_addr(s_flag);
+    const uint32_t vbar_sa = smem_addr(&s_abar[0]), ubar_sa = smem_addr(&s_abar[1]), aflag_sa = smem_addr(&s_aflag[0][0]);
 
     // per-thread constants of the variable side: where this thread's v of every permutation block goes
     uint32_t paddr[NP], prot[NP];                    // quad form: address, right rotation in bits
@@ -560,6 +566,10 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
             const int qv2 = ((int)prm.theta[b] + (int)rank) & 3;
             const int phi2 = prm.phi[b][rank];
             const int t2 = tid + phi2 % NT;
+            if (ASYNC && tid == 0) {
+                s_vbar[ps] = cl_map(vbar_sa, (uint32_t)q);
+                s_ubar[ps] = cl_map(ubar_sa, (uint32_t)qv2);
+            }
             tab[ps * NT + tid] = make_uint2(cl_map(ubuf_sa + (uint32_t)(ps * NT + (t2 & (NT - 1))) * 4u, (uint32_t)qv2),
                                             8u * (uint32_t)((phi2 / NT + (t2 >= NT ? 1 : 0)) & 3));   // check byte k is the variable's byte k + r
         }
@@ -582,11 +592,17 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        if (ASYNC) {
+            mbar_init(&s_abar[0], 1);
+            mbar_init(&s_abar[1], 1);
+        }
         mbar_init_fence();
         if (use_bulk && frame < batch) stage_frame(frame, 0);
     }
     __syncthreads();
+    if (ASYNC) cl_sync();
     unsigned cur = 0, bar_parity = 0;
+    uint32_t apar = 0;
 
     for (; frame < batch; frame += n_clusters) {
         if (tid == 0 && use_bulk && frame + n_clusters < batch) stage_frame(frame + n_clusters, cur ^ 1);
@@ -620,6 +636,7 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
 #pragma unroll
         for (int p = 0; p < NP; p++) ubuf[p * NT + tid] = 0;            // u = 0 before the first iteration
         for (int i = tid; i < HBL; i += NT) hb[i] = 0;
+        if (ASYNC) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         cl_sync();
 
         unsigned iters_run = max_iters;
@@ -649,6 +666,10 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
         };
 
         for (unsigned iter = 0; iter < max_iters; iter++) {
+            if (ASYNC && tid == 0) {
+                mbar_arm(vbar_sa, kVBytes);
+                mbar_arm(ubar_sa, kUBytes);
+            }
             // ================= variable phase (:382-411 and :421) =================
             static_for<0, NCOL>([&](auto ci) {
                 constexpr int c = decltype(ci)::value;
@@ -684,13 +705,15 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
                             uint32_t cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
                             if constexpr (b == 2) {
                                 cv = va * c256 + cv;
-                                cl_st(paddr2[wi], lrot(cv, pswp2[wi]));
+                                if constexpr (ASYNC) cl_st_async(paddr2[wi], lrot(cv, pswp2[wi]), s_vbar[0]);
+                                else cl_st(paddr2[wi], lrot(cv, pswp2[wi]));
                             } else if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
                                 if (wi == 0) hold[k] = cv;
                                 else {
                                     const uint32_t pk = __byte_perm(hold[k], cv, 0x6240);
-                                    cl_st(paddr[ps], __funnelshift_r(pk, pk, prot[ps]));
+                                    if constexpr (ASYNC) cl_st_async(paddr[ps], __funnelshift_r(pk, pk, prot[ps]), s_vbar[ps]);
+                                    else cl_st(paddr[ps], __funnelshift_r(pk, pk, prot[ps]));
                                 }
                             } else {
                                 idm[count_i<P>(b)][wi] = cv;
@@ -699,7 +722,8 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
                     });
                 }
             });
-            cl_sync();
+            if constexpr (ASYNC) mbar_wait_cluster(vbar_sa, apar & 1u);
+            else cl_sync();
 
             // ================= check phase (:391-405 and :422-447) =================
             static_for<0, NROW>([&](auto ri) {
@@ -748,7 +772,8 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
                                     uh[k] = u;
                                 } else {
                                     const uint2 t = tab[count_p<P>(b) * NT + tid];
-                                    cl_st(t.x, lrot(__byte_perm(uh[k], u, 0x6240), t.y));
+                                    if constexpr (ASYNC) cl_st_async(t.x, lrot(__byte_perm(uh[k], u, 0x6240), t.y), s_ubar[count_p<P>(b)]);
+                                    else cl_st(t.x, lrot(__byte_perm(uh[k], u, 0x6240), t.y));
                                 }
                             } else {
                                 idm[count_i<P>(b)][wi] = u;
@@ -762,7 +787,18 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
 #pragma unroll
             for (int wi = 0; wi < WPT; wi++) synd |= bad[wi];
             hb_complete = false;
-            if (!cluster_or(synd != 0)) {
+            bool row0_bad;
+            if constexpr (ASYNC) {
+                const int local = __syncthreads_or(synd != 0);
+                const uint32_t *fl = s_aflag[iter & 1u];
+                if (tid < kCL) cl_st_async(cl_map(aflag_sa + ((iter & 1u) * kCL + rank) * 4u, (uint32_t)tid), (uint32_t)local, cl_map(ubar_sa, (uint32_t)tid));
+                mbar_wait_cluster(ubar_sa, (apar >> 1) & 1u);
+                apar ^= 3u;
+                row0_bad = (fl[0] | fl[1] | fl[2] | fl[3]) != 0;
+            } else {
+                row0_bad = cluster_or(synd != 0);
+            }
+            if (!row0_bad) {
                 flush_pack();
                 hb_complete = true;
                 cl_sync();
@@ -861,7 +897,8 @@ cudaError_t launch_cluster_v(DeviceCtx &ctx, const CodeInfo &c, const void *llrs
     return cudaGetLastError();
 }
 
-// LABRADOR_LDPC_CLUSTER_ASYNC=1: st.async + mbarrier instead of two cluster barriers per iteration (slower, profiles/r02_cluster.md)
+// LABRADOR_LDPC_CLUSTER_ASYNC=1: st.async + mbarrier instead of two cluster barriers per iteration (slower in the pair form:
+// twice the stores, each paying its complete_tx; profiles/r02_cluster.md)
 template <int RATE, int M, int WPT, int MINB>
 cudaError_t launch_cluster(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                            size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
@@ -871,8 +908,8 @@ cudaError_t launch_cluster(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, 
 }
 
 
-template <int RATE, int M, int MINB>
-cudaError_t launch_cluster4(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+template <int RATE, int M, int MINB, bool ASYNC>
+cudaError_t launch_cluster4_v(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                             size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     typedef Proto<RATE> P;
     constexpr int NP = count_p<P>(P::NB);
@@ -881,7 +918,7 @@ cudaError_t launch_cluster4(DeviceCtx &ctx, const CodeInfo &c, const void *llrs,
     // v of block 2 (pairs), v of the other blocks and u (quads), check-side address table, hard-bit words, two staging buffers
     const size_t smem = ((size_t)S + (size_t)(NP - 1) * NT + (size_t)NP * NT + (size_t)2 * NP * NT +
                          (((size_t)P::NCOL * Q / 32 + 3) & ~(size_t)3)) * sizeof(uint32_t) + 2 * (size_t)(P::NCOL - 1) * Q;
-    auto kern = decode_ms_tm_cluster4_kernel<RATE, M, MINB>;
+    auto kern = decode_ms_tm_cluster4_kernel<RATE, M, MINB, ASYNC>;
     static bool configured[kMaxDevices] = {};
     static int clusters_cached[kMaxDevices] = {};
     if (!configured[ctx.device]) {
@@ -908,6 +945,15 @@ cudaError_t launch_cluster4(DeviceCtx &ctx, const CodeInfo &c, const void *llrs,
                                                             (unsigned long long)batch, mi, success, iters, 1u);
     count_launch();
     return cudaGetLastError();
+}
+
+template <int RATE, int M, int MINB>
+cudaError_t launch_cluster4(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
+                            size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
+    // LABRADOR_LDPC_CLUSTER_ASYNC=0: two cluster barriers per iteration instead of st.async + mbarrier (A/B runs and tests)
+    static const bool async = [] { const char *e = getenv("LABRADOR_LDPC_CLUSTER_ASYNC"); return !(e && atoi(e) == 0); }();
+    return async ? launch_cluster4_v<RATE, M, MINB, true>(ctx, c, llrs, output, batch, max_iters, success, iters, stream)
+                 : launch_cluster4_v<RATE, M, MINB, false>(ctx, c, llrs, output, batch, max_iters, success, iters, stream);
 }
 
 }  // namespace

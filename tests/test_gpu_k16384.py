@@ -170,3 +170,26 @@ def test_cluster_kernel_larger_batch_and_unaligned_buffers(ldpc, oracle, code):
         subprocess.check_call([sys.executable, "-c", script, d + "/x.npy", d + "/o.npz"], env=env)
         z = np.load(d + "/o.npz")
         assert_exact((z["out"], z["ok"], z["it"]), oracle.decode_ms_batch(code, llrs[:40], 30, nthreads=16), CODES[code] + " table-driven")
+
+
+@pytest.mark.parametrize("env", [{"LABRADOR_LDPC_CLUSTER_ASYNC": "0"}, {"LABRADOR_LDPC_CLUSTER_QUAD": "0"},
+                                 {"LABRADOR_LDPC_CLUSTER_QUAD": "0", "LABRADOR_LDPC_CLUSTER_ASYNC": "1"},
+                                 {"LABRADOR_LDPC_CLUSTER_MINB": "1"}],
+                         ids=["quad-barriers", "pair-barriers", "pair-async", "quad-async-1cta"])
+def test_cluster_kernel_variants_match_oracle(ldpc, oracle, env):
+    """The shipped kernel packs four messages per word and synchronises through st.async + mbarrier; the earlier forms
+    (two messages per word, two cluster barriers per iteration) stay selectable for A/B runs and must stay exact."""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for code in CODES:
+        _, llrs = frames(ldpc, code, 90, EBN0[code], seed=900 + code, ty="i8")
+        script = ("import sys, numpy as np; sys.path.insert(0, %r); import labrador_ldpc_b200 as L; "
+                  "x = np.load(sys.argv[1]); out, ok, it = L.LDPCCode(%d).decode_ms_batch(x, 40); "
+                  "np.savez(sys.argv[2], out=out, ok=ok, it=it)" % (root, code))
+        with tempfile.TemporaryDirectory() as d:
+            np.save(d + "/x.npy", llrs)
+            subprocess.check_call([sys.executable, "-c", script, d + "/x.npy", d + "/o.npz"],
+                                  env=dict(os.environ, LABRADOR_LDPC_NO_REBUILD="1", **env))
+            z = np.load(d + "/o.npz")
+            assert_exact((z["out"], z["ok"], z["it"]), oracle.decode_ms_batch(code, llrs, 40, nthreads=16),
+                         "%s cluster kernel %r" % (CODES[code], env))
