@@ -56,6 +56,12 @@ using namespace tm;
 
 namespace {
 
+// 0xFFFF in every 16-bit lane whose bit 15 is set
+__device__ __forceinline__ uint32_t prmt_sign15(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(r) : "r"(x));
+    return r;
+}
 __device__ __forceinline__ uint32_t prmt_sign7(uint32_t x) {
     // bytes 0,1 <- sign of byte 0; bytes 2,3 <- sign of byte 2 (bit 7 of each 16-bit lane -> lane mask)
     uint32_t r;
@@ -202,6 +208,12 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 //   ARITH 6: ARITH 5 with |v| and the minima on fp16 lanes: d = C - 127 by one HADD2 (FMA pipe) instead of VABSDIFF4,
 //            |d| as the free operand modifier of HMNMX2 / VHMNMX (KNOBS bit 4: two-input minima only)
 //   ARITH 7: ARITH 6 with the sign-magnitude u of ARITH 4
+//   ARITH 8: ARITH 6 with the self-correction rule on fp16 lanes too (FMA pipe).  The variable side sends 0x6400 + C
+//            (as fp16: 1024 + C, one IMAD); v = 1151 - (1024 + C) by one HADD2 is an integer-valued fp16;
+//            keep = sat(v v_old + 1) (one saturating HFMA2) is 0 exactly where the sign flipped and v_old != 0;
+//            v_cor = v keep + 0 (one HFMA2); mu * 2^-24 (one HMUL2) is the integer the variable side adds.
+//            Five FMA-pipe instructions replace IMAD + LOP3 + PRMT + LOP3 + HADD2; signs are bit 15 of the lanes
+//   ARITH 9: ARITH 8 with the sign of u from an fp16 product (HMUL2 of a +-0 word and v_cor) instead of a LOP3
 //   ARITH 4: ARITH 3 with u sent in sign-magnitude (1 LOP3 + 1 IMAD on the check side) and converted to
 //            two's complement on the FMA pipe by the variable side (fp16 magic-constant add); KNOBS as ARITH 2
 //   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
@@ -352,7 +364,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][wi] = 0;
 #pragma unroll
-            for (int b = 0; b < NB; b++) cc[b][wi] = 0x007f007fu;
+            for (int b = 0; b < NB; b++) cc[b][wi] = (ARITH == 8 || ARITH == 9) ? 0u : 0x007f007fu;
 #pragma unroll
             for (int p = 0; p < NP; p++) msg[p * (M / 2) + wd] = 0;
         }
@@ -474,6 +486,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             if constexpr (ARITH != 2) cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
                             else cv = pmin<CV_F>(f_relu_add(van, ub[k]), 0x00fe00feu);
                             if constexpr (PIGGY && b == 2) cv = va * c256 + cv;          // high byte: the biased marginal
+                            else if constexpr (ARITH == 8 || ARITH == 9) cv = cv * one + 0x64006400u;   // as fp16: 1024 + C
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
                                 msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
@@ -507,8 +520,18 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             if constexpr (PIGGY && b == 2) {
                                 // three marginals of this check: (biased bit 7 of each) XORed = NOT the parity of the hard bits
                                 bad[wi] = ~(hloc8[wi] ^ cv) & 0x80008000u;
-                                cv &= 0x00ff00ffu;
+                                if constexpr (ARITH == 8 || ARITH == 9) cv = (cv & 0x00ff00ffu) | 0x64006400u;
+                                else cv &= 0x00ff00ffu;
                             }
+                            if constexpr (ARITH == 8 || ARITH == 9) {
+                                const __half2 d = __hsub2(u2h(0x647f647fu), u2h(cv));      // 1151 - (1024 + C) = v, an integer-valued fp16 (0 -> +0)
+                                const __half2 keep = __hfma2_sat(d, u2h(cc[b][wi]), u2h(0x3c003c00u));   // sat(v v_old + 1): 0 where the sign flipped and v_old != 0
+                                const __half2 dc = __hfma2(d, keep, u2h(0u));              // killed -> +0
+                                cc[b][wi] = h2u(dc);
+                                ck[k] = h2u(dc);
+                                a[k] = h2u(dc);
+                                sx ^= h2u(dc);                                             // bit 15: product of signs
+                            } else {
                             const uint32_t old = cc[b][wi];
                             const uint32_t x = (cv ^ old) & (cv ^ (old + 0x00010001u));   // bit 7: sign flipped and old != 0
                             const uint32_t km = prmt_sign7(x);
@@ -520,10 +543,12 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                                 a[k] = h2u(__hsub2(u2h(cor), u2h(0x007f007fu)));                 // -v as a signed fp16 lane
                             else a[k] = __vabsdiffu4(cor, 0x007f007fu);                          // |v|
                             sx ^= cor;                                                     // bit 7: product of signs
+                            }
                         }
                     });
+                    if constexpr (ARITH == 9) sx &= 0x80008000u;                          // +-0 in both lanes
                     if constexpr (ARITH == 5) min_excluding_self3<DC>(a, mu);
-                    else if constexpr (ARITH == 6 || ARITH == 7) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
+                    else if constexpr (ARITH >= 6 && ARITH <= 9) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
                     else if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
                     else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
@@ -538,6 +563,14 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             } else if constexpr (ARITH == 3 || ARITH == 5 || ARITH == 6) {
                                 const uint32_t nm = prmt_sign7(sx ^ ck[k]);                // lanes whose u is negative
                                 u = __vadd2(mu[k], nm) ^ nm;                               // +-mu, two's complement
+                            } else if constexpr (ARITH == 8) {
+                                const uint32_t nm = prmt_sign15(sx ^ ck[k]);
+                                const uint32_t mi = h2u(__hmul2(u2h(mu[k]), u2h(0x00010001u)));   // mu * 2^-24: the integer in the low bits
+                                u = __vadd2(mi, nm) ^ nm;
+                            } else if constexpr (ARITH == 9) {
+                                const uint32_t nm = prmt_sign15(h2u(__hmul2(u2h(sx), u2h(ck[k]))));   // the sign of a product survives a zero factor
+                                const uint32_t mi = h2u(__hmul2(u2h(mu[k]), u2h(0x00010001u)));
+                                u = __vadd2(mi, nm) ^ nm;
                             } else {
                                 const uint32_t zs = (sx ^ ck[k]) & 0x00800080u;            // sign of u at bit 7
                                 u = zs * c256 + mu[k];                                     // sign-magnitude: bit 15 | mu
@@ -715,6 +748,8 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
                 if (arith == 632) return launch_tm<RATE, M, 2, 6, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 return launch_tm<RATE, M, 2, 5, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             }
+            if (arith == 832) return launch_tm<RATE, M, 2, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 932) return launch_tm<RATE, M, 2, 9, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 6) return launch_tm<RATE, M, 2, 6, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 632) return launch_tm<RATE, M, 2, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 532) return launch_tm<RATE, M, 2, 5, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -732,6 +767,8 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 5) return launch_tm<RATE, M, 1, 5, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 6) return launch_tm<RATE, M, 1, 6, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 632) return launch_tm<RATE, M, 1, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 832) return launch_tm<RATE, M, 1, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 932) return launch_tm<RATE, M, 1, 9, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 7) return launch_tm<RATE, M, 1, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
         if (arith == 6322) return launch_tm<RATE, M, 1, 6, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
