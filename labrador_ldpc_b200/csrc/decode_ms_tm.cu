@@ -214,6 +214,9 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 //            v_cor = v keep + 0 (one HFMA2); mu * 2^-24 (one HMUL2) is the integer the variable side adds.
 //            Five FMA-pipe instructions replace IMAD + LOP3 + PRMT + LOP3 + HADD2; signs are bit 15 of the lanes
 //   ARITH 9: ARITH 8 with the sign of u from an fp16 product (HMUL2 of a +-0 word and v_cor) instead of a LOP3
+//   ARITH 10: ARITH 8 with u = +-mu by one HFMA2: mu * (+-1.0) + 1536 has the bit pattern 0x6600 +- mu, a per-lane
+//            subtraction leaves the two's-complement message (LOP3 + HFMA2 + VIADD.16x2 instead of
+//            HMUL2 + PRMT + HMUL2 + VIADD.16x2 + LOP3)
 //   ARITH 4: ARITH 3 with u sent in sign-magnitude (1 LOP3 + 1 IMAD on the check side) and converted to
 //            two's complement on the FMA pipe by the variable side (fp16 magic-constant add); KNOBS as ARITH 2
 //   ARITH 2: variable side in fp16 on the FMA pipe, u in sign-magnitude, |v| by VABSDIFF4,
@@ -364,7 +367,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][wi] = 0;
 #pragma unroll
-            for (int b = 0; b < NB; b++) cc[b][wi] = (ARITH == 8 || ARITH == 9) ? 0u : 0x007f007fu;
+            for (int b = 0; b < NB; b++) cc[b][wi] = (ARITH >= 8 && ARITH <= 10) ? 0u : 0x007f007fu;
 #pragma unroll
             for (int p = 0; p < NP; p++) msg[p * (M / 2) + wd] = 0;
         }
@@ -486,7 +489,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             if constexpr (ARITH != 2) cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
                             else cv = pmin<CV_F>(f_relu_add(van, ub[k]), 0x00fe00feu);
                             if constexpr (PIGGY && b == 2) cv = va * c256 + cv;          // high byte: the biased marginal
-                            else if constexpr (ARITH == 8 || ARITH == 9) cv = cv * one + 0x64006400u;   // as fp16: 1024 + C
+                            else if constexpr (ARITH >= 8 && ARITH <= 10) cv = cv * one + 0x64006400u;   // as fp16: 1024 + C
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
                                 msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
@@ -520,10 +523,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             if constexpr (PIGGY && b == 2) {
                                 // three marginals of this check: (biased bit 7 of each) XORed = NOT the parity of the hard bits
                                 bad[wi] = ~(hloc8[wi] ^ cv) & 0x80008000u;
-                                if constexpr (ARITH == 8 || ARITH == 9) cv = (cv & 0x00ff00ffu) | 0x64006400u;
+                                if constexpr (ARITH >= 8 && ARITH <= 10) cv = (cv & 0x00ff00ffu) | 0x64006400u;
                                 else cv &= 0x00ff00ffu;
                             }
-                            if constexpr (ARITH == 8 || ARITH == 9) {
+                            if constexpr (ARITH >= 8 && ARITH <= 10) {
                                 const __half2 d = __hsub2(u2h(0x647f647fu), u2h(cv));      // 1151 - (1024 + C) = v, an integer-valued fp16 (0 -> +0)
                                 const __half2 keep = __hfma2_sat(d, u2h(cc[b][wi]), u2h(0x3c003c00u));   // sat(v v_old + 1): 0 where the sign flipped and v_old != 0
                                 const __half2 dc = __hfma2(d, keep, u2h(0u));              // killed -> +0
@@ -547,8 +550,9 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                         }
                     });
                     if constexpr (ARITH == 9) sx &= 0x80008000u;                          // +-0 in both lanes
+                    if constexpr (ARITH == 10) sx = (sx & 0x80008000u) ^ 0x3c003c00u;     // +-1.0 in both lanes
                     if constexpr (ARITH == 5) min_excluding_self3<DC>(a, mu);
-                    else if constexpr (ARITH >= 6 && ARITH <= 9) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
+                    else if constexpr (ARITH >= 6 && ARITH <= 10) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
                     else if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
                     else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
@@ -567,6 +571,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                                 const uint32_t nm = prmt_sign15(sx ^ ck[k]);
                                 const uint32_t mi = h2u(__hmul2(u2h(mu[k]), u2h(0x00010001u)));   // mu * 2^-24: the integer in the low bits
                                 u = __vadd2(mi, nm) ^ nm;
+                            } else if constexpr (ARITH == 10) {
+                                // +-1.0 with the sign of u; 1536 +- mu has the bits 0x6600 +- mu (ulp 1 in [1024, 2048))
+                                const uint32_t pm = sx ^ (ck[k] & 0x80008000u);
+                                u = __vsub2(h2u(__hfma2(u2h(mu[k]), u2h(pm), u2h(0x66006600u))), 0x66006600u);
                             } else if constexpr (ARITH == 9) {
                                 const uint32_t nm = prmt_sign15(h2u(__hmul2(u2h(sx), u2h(ck[k]))));   // the sign of a product survives a zero factor
                                 const uint32_t mi = h2u(__hmul2(u2h(mu[k]), u2h(0x00010001u)));
@@ -727,10 +735,10 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
 
 }  // namespace
 
-// Variant selection.  Several arithmetic variants are compiled per code; the default (632 = ARITH 6 with the in-thread
+// Variant selection.  Several arithmetic variants are compiled per code; the default (932 = ARITH 9 with the in-thread
 // exit test, KNOBS 32) is the one that measured fastest on B200 for every code (profiles/r02_tm_variants.md).
-// LABRADOR_LDPC_TM_ARITH=1|2|3|4|5|6|7|532|616|632|716 overrides (A/B runs); 52 / 6322 (TM5120 only) = ARITH 5 / 632
-// compiled for 2 resident CTAs per SM (128 registers).
+// LABRADOR_LDPC_TM_ARITH=1|2|3|4|5|6|7|532|616|632|716|832|932 overrides (A/B runs); 52 / 6322 / 9322 (TM5120 only) =
+// ARITH 5 / 632 / 932 compiled for 2 resident CTAs per SM (128 registers).
 template <int RATE, int M>
 cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const void *l, uint8_t *output,
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
@@ -746,10 +754,12 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
                 if (arith == 6) return launch_tm<RATE, M, 2, 6, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 if (arith == 7) return launch_tm<RATE, M, 2, 7, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 if (arith == 632) return launch_tm<RATE, M, 2, 6, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                if (arith == 932) return launch_tm<RATE, M, 2, 9, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 return launch_tm<RATE, M, 2, 5, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             }
             if (arith == 832) return launch_tm<RATE, M, 2, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 932) return launch_tm<RATE, M, 2, 9, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 1032) return launch_tm<RATE, M, 2, 10, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 6) return launch_tm<RATE, M, 2, 6, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 632) return launch_tm<RATE, M, 2, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 532) return launch_tm<RATE, M, 2, 5, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -769,8 +779,10 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 632) return launch_tm<RATE, M, 1, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 832) return launch_tm<RATE, M, 1, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 932) return launch_tm<RATE, M, 1, 9, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 1032) return launch_tm<RATE, M, 1, 10, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 7) return launch_tm<RATE, M, 1, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
+        if (arith == 9322) return launch_tm<RATE, M, 1, 9, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 6322) return launch_tm<RATE, M, 1, 6, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 52) return launch_tm<RATE, M, 1, 5, 0, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     }
@@ -804,39 +816,41 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
     switch (code) {
         case 3:      // TM1280: M = 128, 64 threads per codeword; needs the in-thread exit test (S = 16 < one warp)
             if (!structure_matches<2>(c) || c.m != 128) return false;
-            if (ff) *err = launch_tm_front<2, 128, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 128, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
             else {
                 // resident CTAs per SM the kernel is compiled for (register budget 65536 / 64 / MINB): LABRADOR_LDPC_TM1280_MINB
                 static const int minb = [] { const char *e = getenv("LABRADOR_LDPC_TM1280_MINB"); return e ? atoi(e) : 6; }();
-                if (minb <= 1) *err = launch_tm<2, 128, 1, 6, 32, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-                else if (minb <= 6) *err = launch_tm<2, 128, 1, 6, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-                else *err = launch_tm<2, 128, 1, 6, 32, 8>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                static const int arith = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 932; }();
+                if (arith == 632) *err = launch_tm<2, 128, 1, 6, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else if (minb <= 1) *err = launch_tm<2, 128, 1, 9, 32, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else if (minb <= 6) *err = launch_tm<2, 128, 1, 9, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else *err = launch_tm<2, 128, 1, 9, 32, 8>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             }
             return true;
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            if (ff) *err = launch_tm_front<1, 256, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<1, 256>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 256, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 256>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<0, 512, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<0, 512>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 512, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 512>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<2, 512, 1, 6, 32, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<2, 512>(6322, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 512, 1, 9, 32, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<2, 512>(9322, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            if (ff) *err = launch_tm_front<1, 1024, 1, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<1, 1024>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 1024, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 1024>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            if (ff) *err = launch_tm_front<0, 2048, 2, 6, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<0, 2048>(632, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 2048, 2, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 2048>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;
