@@ -30,6 +30,8 @@ constexpr int kX2Warps = 4;
 
 template <int M> __host__ __device__ constexpr int x2_msg_stride() { return M < 32 ? 32 * M + M : 32 * M; }
 
+__device__ __forceinline__ __half2 x2_u2h(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+__device__ __forceinline__ uint32_t x2_h2u(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 __device__ __forceinline__ uint32_t lane_mask_bit7(uint32_t x) {
     // bytes 0,1 <- sign of byte 0; bytes 2,3 <- sign of byte 2 (bit 7 of each 16-bit lane -> lane mask)
     uint32_t r;
@@ -85,12 +87,18 @@ __device__ __forceinline__ void min_excluding_self8_h(const uint32_t (&a)[8], ui
     mu[7] = x2_hmin2a(p3, a[6]);
 }
 
-template <int M, int FRONT, bool HABS>
+// MODE 0: integer lanes (VABSDIFF4 + VIMNMX); 1: |v| and the minima on fp16 lanes (ARITH 6 of decode_ms_tm.cu);
+// 2: the self-correction rule and the sign of u on fp16 lanes as well (ARITH 10 of decode_ms_tm.cu: the variable side
+// sends 0x6400 + C, v = 1151 - (1024 + C) is an integer-valued fp16, keep = sat(v v_old + 1), v_cor = v keep + 0,
+// u = (mu * +-1.0 + 1536) - 0x6600 per lane) -- FMA-pipe instructions instead of LOP3 / PRMT on the ALU pipe
+template <int M, int FRONT, int MODE>
 __global__ void __launch_bounds__(32 * kX2Warps)
 decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
                          uint8_t *__restrict__ out_all, unsigned long long batch, unsigned max_iters,
                          uint8_t *__restrict__ success, uint32_t *__restrict__ iters_out,
-                         unsigned long long *__restrict__ counter, const float fscale, const float flimit) {
+                         unsigned long long *__restrict__ counter, const float fscale, const float flimit,
+                         const uint32_t one /* == 1: keeps an addition on the FMA pipe (IMAD) */) {
+    constexpr bool HABS = MODE >= 1;
     constexpr int EPT = M > 32 ? M / 32 : 1;        // elements per lane
     constexpr int G = M / EPT;                       // lanes per codeword pair
     constexpr int CWW = 32 / G;                      // codeword pairs per warp
@@ -114,7 +122,7 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
 #pragma unroll
         for (int c = 0; c < 8; c++) Lv[c][ei] = 0x00800080u;
 #pragma unroll
-        for (int b = 0; b < 32; b++) { vold[b][ei] = 0x007f007fu; msg[b * M + sl + ei * G] = 0; }
+        for (int b = 0; b < 32; b++) { vold[b][ei] = MODE == 2 ? 0u : 0x007f007fu; msg[b * M + sl + ei * G] = 0; }
     }
     bool have[2] = {false, false}, exhausted = false;
     unsigned long long frame[2] = {0, 0};
@@ -146,7 +154,7 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     }
 #pragma unroll
                     for (int b = 0; b < 32; b++) {                        // everything zero, every call (:368, :374)
-                        vold[b][ei] = (vold[b][ei] & keep) | (0x7fu << (16 * h));
+                        vold[b][ei] = (vold[b][ei] & keep) | ((MODE == 2 ? 0u : 0x7fu) << (16 * h));
                         msg16[(b * M + e) * 2 + h] = 0;
                     }
                 }
@@ -180,7 +188,8 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     constexpr int b = decltype(bi)::value;
                     if constexpr (tc_blk(b).col == c) {
                         const int i = (j - tc_const_shift<M>(b)) & (M - 1);
-                        msg[b * M + i] = __viaddmin_s16x2_relu(van, ub[tc_pos_in_col(b)], 0x00fe00feu);   // C = 127 - clamp(va - u)
+                        const uint32_t cv = __viaddmin_s16x2_relu(van, ub[tc_pos_in_col(b)], 0x00fe00feu);   // C = 127 - clamp(va - u)
+                        msg[b * M + i] = MODE == 2 ? cv * one + 0x64006400u : cv;                           // MODE 2: as fp16, 1024 + C
                     }
                 });
             });
@@ -200,6 +209,17 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     constexpr int k = decltype(ki)::value;
                     constexpr int b = r * 8 + k;
                     const uint32_t cv = msg[b * M + i];
+                    if constexpr (MODE == 2) {
+                        const __half2 d = __hsub2(x2_u2h(0x647f647fu), x2_u2h(cv));                   // v (0 -> +0)
+                        const __half2 kp = __hfma2_sat(d, x2_u2h(vold[b][ei]), x2_u2h(0x3c003c00u));  // 0 where the sign flipped and v_old != 0
+                        const uint32_t dc = x2_h2u(__hfma2(d, kp, x2_u2h(0u)));                       // killed -> +0
+                        vold[b][ei] = dc;
+                        ck[k] = dc;
+                        a[k] = dc;
+                        sx ^= dc;                                                   // bit 15: product of signs
+                        par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];
+                        return;
+                    }
                     const uint32_t old = vold[b][ei];
                     const uint32_t x = (cv ^ old) & (cv ^ (old + 0x00010001u));     // bit 7: sign flipped and old != 0
                     const uint32_t km = lane_mask_bit7(x);
@@ -218,11 +238,17 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                 par_any |= par;
                 if constexpr (HABS) min_excluding_self8_h(a, mu);
                 else min_excluding_self8(a, mu);
+                if constexpr (MODE == 2) sx = (sx & 0x80008000u) ^ 0x3c003c00u;     // +-1.0 in both halves
                 tc_static_for<0, 8>([&](auto ki) {
                     constexpr int k = decltype(ki)::value;
                     constexpr int b = r * 8 + k;
-                    const uint32_t nm = lane_mask_bit7(sx ^ ck[k]);                 // halves whose u is negative (:398-405)
-                    msg[b * M + i] = __vadd2(mu[k], nm) ^ nm;                       // +-mu, two's complement per half
+                    if constexpr (MODE == 2) {
+                        const uint32_t pm = sx ^ (ck[k] & 0x80008000u);             // +-1.0 with the sign of u (:398-405)
+                        msg[b * M + i] = __vadd2(x2_h2u(__hfma2(x2_u2h(mu[k]), x2_u2h(pm), x2_u2h(0x66006600u))), 0x9a009a00u);
+                    } else {
+                        const uint32_t nm = lane_mask_bit7(sx ^ ck[k]);             // halves whose u is negative (:398-405)
+                        msg[b * M + i] = __vadd2(mu[k], nm) ^ nm;                   // +-mu, two's complement per half
+                    }
                 });
             });
         }
@@ -258,13 +284,13 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
     }
 }
 
-template <int M, int FRONT, bool HABS>
+template <int M, int FRONT, int MODE>
 cudaError_t launch_x2h(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, const Front &front) {
     constexpr int EPT = M > 32 ? M / 32 : 1, G = M / EPT, CWW = 32 / G;
     const size_t warp_bytes = ((4u * CWW * x2_msg_stride<M>() + (size_t)CWW * 8 * M) + 15) & ~(size_t)15;
     const size_t smem = warp_bytes * kX2Warps;
-    auto kern = decode_ms_tc_i8x2_kernel<M, FRONT, HABS>;
+    auto kern = decode_ms_tc_i8x2_kernel<M, FRONT, MODE>;
     static bool configured[kMaxDevices] = {};
     static int per_sm_cached[kMaxDevices] = {};
     if (!configured[ctx.device]) {
@@ -286,18 +312,20 @@ cudaError_t launch_x2h(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
     kern<<<(unsigned)grid, 32 * kX2Warps, smem, stream>>>(
         static_cast<const typename FrontSrc<FRONT, int8_t>::type *>(llrs), output, (unsigned long long)batch, mi,
-        success, iters, counter, front.scale, front.limit);
+        success, iters, counter, front.scale, front.limit, 1u);
     count_launch();
     return cudaGetLastError();
 }
 
-// LABRADOR_LDPC_TC_X2_HABS=0 keeps |v| and the minima on integer lanes (VABSDIFF4 + VIMNMX): A/B runs and tests.
+// LABRADOR_LDPC_TC_X2_HABS=0 keeps everything on integer lanes (VABSDIFF4 + VIMNMX), =1 moves |v| and the minima to fp16
+// lanes, =2 (default) the self-correction rule and the sign of u too: A/B runs and tests.
 template <int M, int FRONT>
 cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, const Front &front) {
-    static const bool habs = [] { const char *e = getenv("LABRADOR_LDPC_TC_X2_HABS"); return !e || atoi(e) != 0; }();
-    if (habs) return launch_x2h<M, FRONT, true>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
-    return launch_x2h<M, FRONT, false>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+    static const int mode = [] { const char *e = getenv("LABRADOR_LDPC_TC_X2_HABS"); return e ? atoi(e) : 2; }();
+    if (mode >= 2) return launch_x2h<M, FRONT, 2>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+    if (mode == 1) return launch_x2h<M, FRONT, 1>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+    return launch_x2h<M, FRONT, 0>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
 }
 
 template <int M>

@@ -574,7 +574,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             } else if constexpr (ARITH == 10) {
                                 // +-1.0 with the sign of u; 1536 +- mu has the bits 0x6600 +- mu (ulp 1 in [1024, 2048))
                                 const uint32_t pm = sx ^ (ck[k] & 0x80008000u);
-                                u = __vsub2(h2u(__hfma2(u2h(mu[k]), u2h(pm), u2h(0x66006600u))), 0x66006600u);
+                                u = __vadd2(h2u(__hfma2(u2h(mu[k]), u2h(pm), u2h(0x66006600u))), 0x9a009a00u);
                             } else if constexpr (ARITH == 9) {
                                 const uint32_t nm = prmt_sign15(h2u(__hmul2(u2h(sx), u2h(ck[k]))));   // the sign of a product survives a zero factor
                                 const uint32_t mi = h2u(__hmul2(u2h(mu[k]), u2h(0x00010001u)));
@@ -735,10 +735,10 @@ cudaError_t launch_tm(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8
 
 }  // namespace
 
-// Variant selection.  Several arithmetic variants are compiled per code; the default (932 = ARITH 9 with the in-thread
+// Variant selection.  Several arithmetic variants are compiled per code; the default (1032 = ARITH 10 with the in-thread
 // exit test, KNOBS 32) is the one that measured fastest on B200 for every code (profiles/r02_tm_variants.md).
-// LABRADOR_LDPC_TM_ARITH=1|2|3|4|5|6|7|532|616|632|716|832|932 overrides (A/B runs); 52 / 6322 / 9322 (TM5120 only) =
-// ARITH 5 / 632 / 932 compiled for 2 resident CTAs per SM (128 registers).
+// LABRADOR_LDPC_TM_ARITH=1|2|3|4|5|6|7|532|616|632|716|832|932|1032 overrides (A/B runs); 52 / 6322 / 9322 / 10322
+// (TM5120 only) = ARITH 5 / 632 / 932 / 1032 compiled for 2 resident CTAs per SM (128 registers).
 template <int RATE, int M>
 cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo &c, const void *l, uint8_t *output,
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
@@ -755,6 +755,7 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
                 if (arith == 7) return launch_tm<RATE, M, 2, 7, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 if (arith == 632) return launch_tm<RATE, M, 2, 6, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 if (arith == 932) return launch_tm<RATE, M, 2, 9, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                if (arith == 1032) return launch_tm<RATE, M, 2, 10, 32, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 return launch_tm<RATE, M, 2, 5, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             }
             if (arith == 832) return launch_tm<RATE, M, 2, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -782,6 +783,7 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 1032) return launch_tm<RATE, M, 1, 10, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 7) return launch_tm<RATE, M, 1, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
+        if (arith == 10322) return launch_tm<RATE, M, 1, 10, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 9322) return launch_tm<RATE, M, 1, 9, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 6322) return launch_tm<RATE, M, 1, 6, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 52) return launch_tm<RATE, M, 1, 5, 0, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -816,41 +818,41 @@ bool launch_decode_ms_tm_i8(DeviceCtx &ctx, int code, const void *llrs, uint8_t 
     switch (code) {
         case 3:      // TM1280: M = 128, 64 threads per codeword; needs the in-thread exit test (S = 16 < one warp)
             if (!structure_matches<2>(c) || c.m != 128) return false;
-            if (ff) *err = launch_tm_front<2, 128, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 128, 1, 10, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
             else {
                 // resident CTAs per SM the kernel is compiled for (register budget 65536 / 64 / MINB): LABRADOR_LDPC_TM1280_MINB
                 static const int minb = [] { const char *e = getenv("LABRADOR_LDPC_TM1280_MINB"); return e ? atoi(e) : 6; }();
-                static const int arith = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 932; }();
+                static const int arith = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 1032; }();
                 if (arith == 632) *err = launch_tm<2, 128, 1, 6, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-                else if (minb <= 1) *err = launch_tm<2, 128, 1, 9, 32, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-                else if (minb <= 6) *err = launch_tm<2, 128, 1, 9, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
-                else *err = launch_tm<2, 128, 1, 9, 32, 8>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else if (minb <= 1) *err = launch_tm<2, 128, 1, 10, 32, 1>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else if (minb <= 6) *err = launch_tm<2, 128, 1, 10, 32, 6>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+                else *err = launch_tm<2, 128, 1, 10, 32, 8>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             }
             return true;
         case 4:
             if (!structure_matches<1>(c) || c.m != 256) return false;
-            if (ff) *err = launch_tm_front<1, 256, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<1, 256>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 256, 1, 10, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 256>(1032, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 5:
             if (!structure_matches<0>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<0, 512, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<0, 512>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 512, 1, 10, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 512>(1032, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 6:
             if (!structure_matches<2>(c) || c.m != 512) return false;
-            if (ff) *err = launch_tm_front<2, 512, 1, 9, 32, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<2, 512>(9322, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<2, 512, 1, 10, 32, 2>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<2, 512>(10322, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 7:
             if (!structure_matches<1>(c) || c.m != 1024) return false;
-            if (ff) *err = launch_tm_front<1, 1024, 1, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<1, 1024>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<1, 1024, 1, 10, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<1, 1024>(1032, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         case 8:
             if (!structure_matches<0>(c) || c.m != 2048) return false;
-            if (ff) *err = launch_tm_front<0, 2048, 2, 9, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
-            else *err = launch_tm_variant<0, 2048>(932, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (ff) *err = launch_tm_front<0, 2048, 2, 10, 32, 1>(front, ctx, c, l, output, batch, max_iters, success, iters, stream);
+            else *err = launch_tm_variant<0, 2048>(1032, ctx, c, l, output, batch, max_iters, success, iters, stream);
             return true;
         default:
             return false;

@@ -631,7 +631,7 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][wi] = 0;
 #pragma unroll
-            for (int b = 0; b < NB; b++) cc[b][wi] = 0x007f007fu;
+            for (int b = 0; b < NB; b++) cc[b][wi] = 0;                  // v_old = +0 (fp16 lanes)
         }
 #pragma unroll
         for (int p = 0; p < NP; p++) ubuf[p * NT + tid] = 0;            // u = 0 before the first iteration
@@ -716,7 +716,7 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
                                     else cl_st(paddr[ps], __funnelshift_r(pk, pk, prot[ps]));
                                 }
                             } else {
-                                idm[count_i<P>(b)][wi] = cv;
+                                idm[count_i<P>(b)][wi] = cv * one + 0x64006400u;           // as fp16: 1024 + C
                             }
                         }
                     });
@@ -743,30 +743,34 @@ decode_ms_tm_cluster4_kernel(const TmParams prm, const int8_t *__restrict__ llrs
                             if constexpr (b == 2) {
                                 cv = msg2[wv];
                                 bad[wi] = ~(hloc8[wi] ^ cv) & 0x80008000u;
-                                cv &= 0x00ff00ffu;
+                                cv = (cv & 0x00ff00ffu) | 0x64006400u;
                             } else if constexpr (P::blk(b).isp) {
                                 const uint32_t pq = msg4[(count_p<P>(b) - 1) * NT + tid];   // four unsigned bytes
-                                cv = wi == 0 ? __byte_perm(pq, 0, 0x4240) : __byte_perm(pq, 0, 0x4341);
+                                cv = wi == 0 ? __byte_perm(pq, 0x64646464u, 0x4240) : __byte_perm(pq, 0x64646464u, 0x4341);   // 0x6400 + C in both lanes
                             } else {
                                 cv = idm[count_i<P>(b)][wi];
                             }
-                            const uint32_t old = cc[b][wi];
-                            const uint32_t x = (cv ^ old) & (cv ^ (old + 0x00010001u));
-                            const uint32_t km = sign7_mask(x);
-                            const uint32_t cor = (cv & ~km) | (0x007f007fu & km);
-                            cc[b][wi] = cor;
-                            ck[k] = cor;
-                            a[k] = ch2u(__hsub2(cu2h(cor), cu2h(0x007f007fu)));
-                            sx ^= cor;
+                            // the arithmetic of ARITH 10 (decode_ms_tm.cu): v = 1151 - (1024 + C) as an integer-valued fp16,
+                            // keep = sat(v v_old + 1) is 0 exactly where the sign flipped and v_old != 0, v_cor = v keep + 0
+                            const __half2 d = __hsub2(cu2h(0x647f647fu), cu2h(cv));
+                            const __half2 kp = __hfma2_sat(d, cu2h(cc[b][wi]), cu2h(0x3c003c00u));
+                            const uint32_t dc = ch2u(__hfma2(d, kp, cu2h(0u)));
+                            cc[b][wi] = dc;
+                            ck[k] = dc;
+                            a[k] = dc;
+                            sx ^= dc;                                                      // bit 15: product of signs
                         }
                     });
                     min_excl_h<DC>(a, mu);
+                    sx = (sx & 0x80008000u) ^ 0x3c003c00u;                                 // +-1.0 in both lanes
                     static_for<0, NB>([&](auto bi) {
                         constexpr int b = decltype(bi)::value;
                         if constexpr (P::blk(b).row == r) {
                             constexpr int k = pos_in_row<P>(b);
-                            const uint32_t nm = sign7_mask(sx ^ ck[k]);
-                            const uint32_t u = __vadd2(mu[k], nm) ^ nm;
+                            // mu * +-1.0 + 1536 has the bit pattern 0x6600 +- mu: minus 0x6600 per lane = u in two's complement (written as
+                            // an addition: __vsub2 makes ptxas build its constant in a register, wrongly in one instantiation)
+                            const uint32_t pm = sx ^ (ck[k] & 0x80008000u);
+                            const uint32_t u = __vadd2(ch2u(__hfma2(cu2h(mu[k]), cu2h(pm), cu2h(0x66006600u))), 0x9a009a00u);
                             if constexpr (P::blk(b).isp) {
                                 if (wi == 0) {
                                     uh[k] = u;
