@@ -104,7 +104,9 @@ def read_ncu():
         return {"dram_bytes": dram, "frames": meta["frames"], "edge_updates": meta["edge_updates"],
                 "alu_busy": val("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active") / 100.0,
                 "sm_cycles": val("sm__cycles_active.avg"), "kernel": meta.get("kernel", ""),
-                "issue_active": val("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0}
+                "issue_active": val("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0,
+                "inst_executed": val("smsp__inst_executed.sum"),
+                "fmaheavy_busy": val("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed") / 100.0}
     except Exception:
         return None
 
@@ -687,28 +689,38 @@ def main():
         line["llr_checksum"] = {"rank0_sum_of_int32_words": int(parts[0].inp.view(torch.int32).sum(dtype=torch.int64).item())}
         ncu = read_ncu()
         lane_peak = 148 * 64 * f_max                    # ALU pipe: 16 lanes per SM sub-partition per clock (profiles/r01_pipe_ubench.md)
+        issue_peak = 148 * 4 * f_max                    # one warp-instruction per SM sub-partition per clock
         alu = {"edge_pass_updates_per_s": upd_per_gpu_s, "peak": lane_peak, "unit": "lane-op/s",
                "peak_source": "148 SMs x 64 ALU-pipe lanes x sm_max_mhz",
                "note": "per GPU; one edge-pass update = one trip of either edge loop of src/decoder.rs:388-450"}
+        issue = {"peak": issue_peak, "unit": "warp-instr/s", "peak_source": "148 SMs x 4 schedulers x sm_max_mhz"}
         if ncu:
             # ALU-pipe warp-instructions of the captured launch = busy fraction x 2 per clock per SM x active cycles x SMs
             alu_inst = ncu["alu_busy"] * 2.0 * ncu["sm_cycles"] * 148
             per_update = alu_inst / ncu["edge_updates"]
             achieved = per_update * upd_per_gpu_s * 32.0
+            src = "profiles/r02_tm8192_ncu.csv (raw ncu export of %s) + profiles/r02_tm8192_ncu.json" % ncu["kernel"]
             alu.update({"achieved": achieved, "frac": achieved / lane_peak,
                         "alu_pipe_warp_instr_per_edge_update": per_update,
-                        "alu_pipe_busy_frac_in_capture": ncu["alu_busy"], "issue_active_frac_in_capture": ncu["issue_active"],
-                        "source": "profiles/r02_tm8192_ncu.csv (raw ncu export of %s) + profiles/r02_tm8192_ncu.json" % ncu["kernel"]})
+                        "alu_pipe_busy_frac_in_capture": ncu["alu_busy"], "source": src})
+            # every warp-instruction of the captured launch takes one issue slot
+            inst_per_update = ncu["inst_executed"] / ncu["edge_updates"]
+            issue.update({"achieved": inst_per_update * upd_per_gpu_s, "frac": inst_per_update * upd_per_gpu_s / issue_peak,
+                          "warp_instr_per_edge_update": inst_per_update, "issue_active_frac_in_capture": ncu["issue_active"],
+                          "fma_heavy_pipe_busy_frac_in_capture": ncu["fmaheavy_busy"], "source": src})
             roofline["traffic"] = ncu["dram_bytes"] / ncu["frames"] * parts[0].frames
             roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum of the tracked capture (%d frames), "
                                           "per frame, times this launch's frames" % ncu["frames"])
-        roofline = {"bound": "alu_pipe", "achieved": alu.get("achieved"), "peak": lane_peak, "unit": "lane-op/s",
-                    "frac": alu.get("frac"), "traffic": roofline["traffic"], "alu": alu,
+        roofline = {"bound": "issue_slots", "achieved": issue.get("achieved"), "peak": issue_peak, "unit": "warp-instr/s",
+                    "frac": issue.get("frac"), "traffic": roofline["traffic"], "issue": issue, "alu": alu,
                     "hbm": {k: roofline[k] for k in ("achieved", "peak", "unit", "frac", "peak_source")},
                     "traffic_source": roofline.get("traffic_source"), "kernel_of": roofline["kernel_of"],
                     "share_of_step": 1.0,
-                    "note": "decode_ms is bound by the integer ALU pipe, not HBM (DESIGN.md 4.1): the primary fraction is "
-                            "ALU-pipe lane-ops against 148 x 64 lanes x f_max, the HBM figure is secondary"}
+                    "note": "decode_ms is an instruction-throughput kernel, not an HBM one (DESIGN.md 4.1).  Since the "
+                            "self-correction rule and the sign of u moved to fp16 lanes the work is spread over the ALU pipe "
+                            "and the FMA-heavy pipe, and the most utilised resource is the issue slots: the primary fraction "
+                            "is warp-instructions issued against 148 SMs x 4 schedulers x f_max; the ALU-pipe fraction "
+                            "(the primary one until the fp16 rewrite) and the HBM figure are secondary"}
     line["roofline"] = roofline
 
     if not args.no_cpu_baseline:
