@@ -20,8 +20,13 @@
 //   * the two barriers of an iteration become cluster barriers (barrier.cluster arrive.release / wait.acquire, which
 //     also order the remote stores), and the exit decision is an OR over the four CTAs (one flag word per CTA, written
 //     into every CTA's shared memory before the barrier that the next phase needs anyway).
-// Everything inside a CTA is the shipped arithmetic of decode_ms_tm.cu (ARITH 6 + KNOBS 32): biased s16x2 lanes,
-// VIADDMNMX saturating adds, fp16 |v| and minima, self-correction by bit test, row-0 exit test in the threads that own
+// Two kernels follow.  decode_ms_tm_cluster_kernel is the form described so far (two messages per 32-bit word, the
+// integer self-correction rule: ARITH 6 + KNOBS 32 of decode_ms_tm.cu), kept for A/B runs and tests
+// (LABRADOR_LDPC_CLUSTER_QUAD=0).  decode_ms_tm_cluster4_kernel is the one that ships: FOUR messages per word (half the
+// stores and bytes across the cluster), completion of a phase by BYTE COUNT -- st.async stores that complete on an
+// mbarrier of the receiving CTA, so an iteration contains no cluster barrier -- and the check side as exact fp16
+// arithmetic (ARITH 10 of decode_ms_tm.cu).  Measurements of every step: profiles/r02_cluster.md.
+// In both: biased s16x2 lanes, VIADDMNMX saturating adds, fp16 |v| and minima, row-0 exit test in the threads that own
 // the checks with the permuted marginal riding in the message's high byte; rows 1-2 only when row 0 is clean, from
 // ballot-packed hard bits (the other quarters' words are read through distributed shared memory).  Each CTA stages its
 // quarter of the next frame (one bulk asynchronous copy per data column) while the current frame is decoded.
@@ -148,8 +153,7 @@ __global__ void __cluster_dims__(kCL, 1, 1) __launch_bounds__(M / 8 / WPT, MINB)
 decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_all, uint8_t *__restrict__ out_all,
                             unsigned long long batch, unsigned max_iters, uint8_t *__restrict__ success,
                             uint32_t *__restrict__ iters_out,
-                            const uint32_t one /* == 1: keeps carry-free packing and subtractions on the FMA pipe (IMAD) */,
-                            const uint32_t remote /* all ones; 0 (timing experiments only, results wrong): every push stays in the own CTA */) {
+                            const uint32_t one /* == 1: keeps carry-free packing and subtractions on the FMA pipe (IMAD) */) {
     typedef Proto<RATE> P;
     constexpr int NB = P::NB, NCOL = P::NCOL, NROW = P::NROW;
     constexpr int NP = count_p<P>(NB), NI = NB - NP;
@@ -198,18 +202,18 @@ decode_ms_tm_cluster_kernel(const TmParams prm, const int8_t *__restrict__ llrs_
                 const int phi_lo = phi % S, phi_hi = phi / S;
                 const int borrow = wv < phi_lo ? 1 : 0;
                 const int w = (wv - phi_lo) & (S - 1);
-                paddr[ps][wi] = cl_map(msg_sa + (uint32_t)(ps * S + w) * 4u, ((uint32_t)q & remote) | (rank & ~remote));
+                paddr[ps][wi] = cl_map(msg_sa + (uint32_t)(ps * S + w) * 4u, (uint32_t)q);
                 pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 16u : 0u;
                 // the same block seen from the check this thread owns (quarter `rank`, slot wv): the variable pair it talks to
                 const int qv2 = ((int)prm.theta[b] + (int)rank) & 3;
                 const int phi2 = prm.phi[b][rank];
                 const int t2 = wv + phi2 % S;                                 // carry out of the half quarter <=> the var side's borrow
                 const int wv2 = t2 & (S - 1);
-                tab[(ps * WPT + wi) * NT + tid] = make_uint2(cl_map(ubuf_sa + (uint32_t)(ps * S + wv2) * 4u, ((uint32_t)qv2 & remote) | (rank & ~remote)),
+                tab[(ps * WPT + wi) * NT + tid] = make_uint2(cl_map(ubuf_sa + (uint32_t)(ps * S + wv2) * 4u, (uint32_t)qv2),
                                                              (((phi2 / S) ^ (t2 >= S ? 1 : 0)) & 1) ? 16u : 0u);
                 if (ASYNC && tid == 0 && wi == 0) {
-                    s_vbar[ps] = cl_map(vbar_sa, ((uint32_t)q & remote) | (rank & ~remote));
-                    s_ubar[ps] = cl_map(ubar_sa, ((uint32_t)qv2 & remote) | (rank & ~remote));
+                    s_vbar[ps] = cl_map(vbar_sa, (uint32_t)q);
+                    s_ubar[ps] = cl_map(ubar_sa, (uint32_t)qv2);
                 }
             }
         });
@@ -893,10 +897,8 @@ cudaError_t launch_cluster_v(DeviceCtx &ctx, const CodeInfo &c, const void *llrs
     unsigned long long clusters = (unsigned long long)clusters_cached[ctx.device];
     if (clusters > batch) clusters = batch;
     const unsigned mi = max_iters > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)max_iters;
-    // LABRADOR_LDPC_CLUSTER_LOCAL_PUSH=1: timing experiment (profiles/r02_cluster.md), decodes garbage
-    static const uint32_t remote = [] { const char *e = getenv("LABRADOR_LDPC_CLUSTER_LOCAL_PUSH"); return (e && atoi(e) != 0) ? 0u : 0xFFFFFFFFu; }();
     kern<<<(unsigned)(clusters * kCL), NT, smem, stream>>>(prm, static_cast<const int8_t *>(llrs), output,
-                                                            (unsigned long long)batch, mi, success, iters, 1u, remote);
+                                                            (unsigned long long)batch, mi, success, iters, 1u);
     count_launch();
     return cudaGetLastError();
 }
