@@ -90,7 +90,10 @@ __device__ __forceinline__ void min_excluding_self8_h(const uint32_t (&a)[8], ui
 // MODE 0: integer lanes (VABSDIFF4 + VIMNMX); 1: |v| and the minima on fp16 lanes (ARITH 6 of decode_ms_tm.cu);
 // 2: the self-correction rule and the sign of u on fp16 lanes as well (ARITH 10 of decode_ms_tm.cu: the variable side
 // sends 0x6400 + C, v = 1151 - (1024 + C) is an integer-valued fp16, keep = sat(v v_old + 1), v_cor = v keep + 0,
-// u = (mu * +-1.0 + 1536) - 0x6600 per lane) -- FMA-pipe instructions instead of LOP3 / PRMT on the ALU pipe
+// u = (mu * +-1.0 + 1536) - 0x6600 per lane) -- FMA-pipe instructions instead of LOP3 / PRMT on the ALU pipe;
+// 3: MODE 2 with the hard decision of the sending variable in bit 15 of every message lane (|.| is a free operand
+// modifier of the HADD2 that reads it), so the parity of a check (:445-447) is the XOR of the words it reads anyway: no
+// hard-bit bytes in shared memory, no byte load per edge; the output bits are ballots of the marginals' sign bits
 template <int M, int FRONT, int MODE>
 __global__ void __launch_bounds__(32 * kX2Warps)
 decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restrict__ llrs_all,
@@ -117,12 +120,13 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
     const unsigned group_mask = (G == 32 ? kFull : ((1u << G) - 1u)) << (cwl * G);
 
     uint32_t Lv[8][EPT], vold[32][EPT];
+    uint32_t hp[4][EPT];                             // MODE 3: bits 15 / 31 (even column) and 16 / 0 (odd column): hard decisions of the two codewords
 #pragma unroll
     for (int ei = 0; ei < EPT; ei++) {
 #pragma unroll
         for (int c = 0; c < 8; c++) Lv[c][ei] = 0x00800080u;
 #pragma unroll
-        for (int b = 0; b < 32; b++) { vold[b][ei] = MODE == 2 ? 0u : 0x007f007fu; msg[b * M + sl + ei * G] = 0; }
+        for (int b = 0; b < 32; b++) { vold[b][ei] = MODE >= 2 ? 0u : 0x007f007fu; msg[b * M + sl + ei * G] = 0; }
     }
     bool have[2] = {false, false}, exhausted = false;
     unsigned long long frame[2] = {0, 0};
@@ -154,7 +158,7 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     }
 #pragma unroll
                     for (int b = 0; b < 32; b++) {                        // everything zero, every call (:368, :374)
-                        vold[b][ei] = (vold[b][ei] & keep) | ((MODE == 2 ? 0u : 0x7fu) << (16 * h));
+                        vold[b][ei] = (vold[b][ei] & keep) | ((MODE >= 2 ? 0u : 0x7fu) << (16 * h));
                         msg16[(b * M + e) * 2 + h] = 0;
                     }
                 }
@@ -182,14 +186,22 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                 });
                 // hard decision: va < 0  <=>  VA < 128  <=>  bit 7 clear
                 const uint32_t nb = ~va;
-                hbv[c * M + j] = (uint8_t)(((nb >> 7) & 1u) | ((nb >> 22) & 2u));
+                uint32_t magic = 0x64006400u;
+                if constexpr (MODE == 3) {
+                    const uint32_t hbit = (nb & 0x00800080u) * (one << 8);           // bits 15 / 31: the hard decisions
+                    magic = hbit + 0x64006400u;                                      // as fp16: -(1024 + C) where the bit is 1
+                    if constexpr ((c & 1) == 0) hp[c / 2][ei] = hbit;
+                    else hp[c / 2][ei] += __funnelshift_l(hbit, hbit, 1);            // bits 16 / 0
+                } else {
+                    hbv[c * M + j] = (uint8_t)(((nb >> 7) & 1u) | ((nb >> 22) & 2u));
+                }
                 const uint32_t van = 0x00ff00ffu - va;
                 tc_static_for<0, 32>([&](auto bi) {
                     constexpr int b = decltype(bi)::value;
                     if constexpr (tc_blk(b).col == c) {
                         const int i = (j - tc_const_shift<M>(b)) & (M - 1);
                         const uint32_t cv = __viaddmin_s16x2_relu(van, ub[tc_pos_in_col(b)], 0x00fe00feu);   // C = 127 - clamp(va - u)
-                        msg[b * M + i] = MODE == 2 ? cv * one + 0x64006400u : cv;                           // MODE 2: as fp16, 1024 + C
+                        msg[b * M + i] = MODE >= 2 ? cv * one + magic : cv;                                 // MODE 2, 3: as fp16, +-(1024 + C)
                     }
                 });
             });
@@ -209,15 +221,17 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     constexpr int k = decltype(ki)::value;
                     constexpr int b = r * 8 + k;
                     const uint32_t cv = msg[b * M + i];
-                    if constexpr (MODE == 2) {
-                        const __half2 d = __hsub2(x2_u2h(0x647f647fu), x2_u2h(cv));                   // v (0 -> +0)
+                    if constexpr (MODE >= 2) {
+                        const __half2 d = MODE == 3 ? __hsub2(x2_u2h(0x647f647fu), __habs2(x2_u2h(cv)))
+                                                    : __hsub2(x2_u2h(0x647f647fu), x2_u2h(cv));       // v (0 -> +0)
                         const __half2 kp = __hfma2_sat(d, x2_u2h(vold[b][ei]), x2_u2h(0x3c003c00u));  // 0 where the sign flipped and v_old != 0
                         const uint32_t dc = x2_h2u(__hfma2(d, kp, x2_u2h(0u)));                       // killed -> +0
                         vold[b][ei] = dc;
                         ck[k] = dc;
                         a[k] = dc;
                         sx ^= dc;                                                   // bit 15: product of signs
-                        par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];
+                        if constexpr (MODE == 3) par ^= cv;                         // bits 15 / 31: parity of the hard decisions
+                        else par ^= hbv[tc_blk(b).col * M + ((i + tc_const_shift<M>(b)) & (M - 1))];
                         return;
                     }
                     const uint32_t old = vold[b][ei];
@@ -238,11 +252,11 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                 par_any |= par;
                 if constexpr (HABS) min_excluding_self8_h(a, mu);
                 else min_excluding_self8(a, mu);
-                if constexpr (MODE == 2) sx = (sx & 0x80008000u) ^ 0x3c003c00u;     // +-1.0 in both halves
+                if constexpr (MODE >= 2) sx = (sx & 0x80008000u) ^ 0x3c003c00u;     // +-1.0 in both halves
                 tc_static_for<0, 8>([&](auto ki) {
                     constexpr int k = decltype(ki)::value;
                     constexpr int b = r * 8 + k;
-                    if constexpr (MODE == 2) {
+                    if constexpr (MODE >= 2) {
                         const uint32_t pm = sx ^ (ck[k] & 0x80008000u);             // +-1.0 with the sign of u (:398-405)
                         msg[b * M + i] = __vadd2(x2_h2u(__hfma2(x2_u2h(mu[k]), x2_u2h(pm), x2_u2h(0x66006600u))), 0x9a009a00u);
                     } else {
@@ -252,8 +266,8 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                 });
             });
         }
-        const unsigned bad0 = __ballot_sync(kFull, (par_any & 1u) != 0) & group_mask;
-        const unsigned bad1 = __ballot_sync(kFull, (par_any & 2u) != 0) & group_mask;
+        const unsigned bad0 = __ballot_sync(kFull, (par_any & (MODE == 3 ? 0x00008000u : 1u)) != 0) & group_mask;
+        const unsigned bad1 = __ballot_sync(kFull, (par_any & (MODE == 3 ? 0x80000000u : 2u)) != 0) & group_mask;
         bool fin[2] = {false, false}, ok[2] = {false, false};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -263,9 +277,28 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
             }
         }
         // ---- output of the halves that are done: hard decisions MSB first (:455-461, :466-473) ----
+        if constexpr (MODE == 3) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (!__any_sync(kFull, fin[h])) continue;                // warp-uniform: every lane takes part in the ballots
+                uint8_t *out = out_all + frame[h] * (unsigned long long)(N / 8);
+#pragma unroll
+                for (int ei = 0; ei < EPT; ei++) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        // hard decision of element sl + ei * G of column c, codeword h (see the variable phase)
+                        const uint32_t w = hp[c / 2][ei];
+                        const bool hard = (c & 1) ? ((w >> (h ? 0 : 16)) & 1u) != 0 : ((w >> (h ? 31 : 15)) & 1u) != 0;
+                        const unsigned bal = __ballot_sync(kFull, hard) >> (cwl * G);
+                        if (fin[h] && sl < G / 8)                        // byte sl of this column: elements 8 sl .. 8 sl + 7, first element = MSB
+                            out[(c * M + ei * G) / 8 + sl] = (uint8_t)(__brev((bal >> (8 * sl)) & 0xFFu) >> 24);
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            if (fin[h]) {
+            if (MODE != 3 && fin[h]) {
                 have[h] = false;
                 uint8_t *out = out_all + frame[h] * (unsigned long long)(N / 8);
                 for (int o = sl; o < N / 8; o += G) {
@@ -274,6 +307,13 @@ decode_ms_tc_i8x2_kernel(const typename FrontSrc<FRONT, int8_t>::type *__restric
                     for (int bit = 0; bit < 8; bit++) byte |= (((unsigned)hbv[o * 8 + bit] >> h) & 1u) << (7 - bit);
                     out[o] = (uint8_t)byte;
                 }
+                if (sl == 0) {
+                    if (success) success[frame[h]] = ok[h] ? 1 : 0;
+                    if (iters_out) iters_out[frame[h]] = ok[h] ? iter[h] : max_iters;
+                }
+            }
+            if (MODE == 3 && fin[h]) {
+                have[h] = false;
                 if (sl == 0) {
                     if (success) success[frame[h]] = ok[h] ? 1 : 0;
                     if (iters_out) iters_out[frame[h]] = ok[h] ? iter[h] : max_iters;
@@ -318,12 +358,15 @@ cudaError_t launch_x2h(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint
 }
 
 // LABRADOR_LDPC_TC_X2_HABS=0 keeps everything on integer lanes (VABSDIFF4 + VIMNMX), =1 moves |v| and the minima to fp16
-// lanes, =2 (default) the self-correction rule and the sign of u too: A/B runs and tests.
+// lanes, =2 the self-correction rule and the sign of u too (default for TC256 / TC512), =3 also the hard decisions inside
+// the messages (default for TC128): A/B runs and tests.
 template <int M, int FRONT>
 cudaError_t launch_x2(DeviceCtx &ctx, const CodeInfo &c, const void *llrs, uint8_t *output, size_t batch,
                       size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream, const Front &front) {
-    static const int mode = [] { const char *e = getenv("LABRADOR_LDPC_TC_X2_HABS"); return e ? atoi(e) : 2; }();
-    if (mode >= 2) return launch_x2h<M, FRONT, 2>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+    // default: 3 for TC128 (+1-5 %), 2 for TC256 / TC512 (MODE 3 is 0.5-1.6 % slower there: profiles/raw/r02ah_tc_x2_mode3_log.txt)
+    static const int mode = [] { const char *e = getenv("LABRADOR_LDPC_TC_X2_HABS"); return e ? atoi(e) : (M == 16 ? 3 : 2); }();
+    if (mode >= 3) return launch_x2h<M, FRONT, 3>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
+    if (mode == 2) return launch_x2h<M, FRONT, 2>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
     if (mode == 1) return launch_x2h<M, FRONT, 1>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
     return launch_x2h<M, FRONT, 0>(ctx, c, llrs, output, batch, max_iters, success, iters, stream, front);
 }
