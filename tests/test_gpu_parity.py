@@ -801,3 +801,40 @@ def test_many_async_launches_on_several_streams(ldpc, oracle):
     torch.cuda.synchronize()
     for got, want, name in results:
         assert_exact([g.cpu().numpy() for g in got], want, "async " + name)
+
+
+@pytest.mark.parametrize("env", [{"LABRADOR_LDPC_TC_X2_HABS": "0"}, {"LABRADOR_LDPC_TC_X2_HABS": "1"},
+                                 {"LABRADOR_LDPC_TC_X2_HABS": "2"}, {"LABRADOR_LDPC_TC_X2_HABS": "3"},
+                                 {"LABRADOR_LDPC_TM_ARITH": "632"}, {"LABRADOR_LDPC_TM_ARITH": "932"},
+                                 {"LABRADOR_LDPC_TM_ARITH": "5"}, {"LABRADOR_LDPC_TM_WPT": "1"}],
+                         ids=["tc-int", "tc-fp16-minima", "tc-fp16-check-side", "tc-hard-bits-in-messages",
+                              "tm-arith-632", "tm-arith-932", "tm-arith-5", "tm8192-one-slot-per-thread"])
+def test_i8_min_sum_arithmetic_variants_stay_exact(env):
+    """The i8 min-sum kernels keep their earlier arithmetic forms selectable (integer lanes, fp16 only for the minima,
+    fp16 check side, hard decisions inside the messages): every one of them must reproduce the oracle bit for bit,
+    including frames that saturate and frames that run into the iteration cap."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    codes = (0, 1, 2) if "LABRADOR_LDPC_TC_X2_HABS" in env else (3, 4, 5, 6, 7, 8)
+    script = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/oracle"); sys.path.insert(0, %r + "/tests")
+import labrador_ldpc_b200 as L, pyoracle
+from frames import make_frames
+o = pyoracle.Oracle()
+EB = {0: 2.0, 1: 2.0, 2: 1.8, 3: 3.4, 4: 2.4, 5: 1.6, 6: 3.4, 7: 2.4, 8: 1.6}
+for code in %r:
+    c = L.LDPCCode(code)
+    _, _, llrs = make_frames(o, code, 203, EB[code], seed=77 + code, ty="i8")
+    rng = np.random.default_rng(code)
+    llrs[:8] = rng.integers(-128, 128, llrs[:8].shape).astype(np.int8)        # saturation stress, never converges
+    llrs[8, :] = -128
+    for mi in (25, 2):
+        want = o.decode_ms_batch(code, llrs, mi, nthreads=16)
+        got = c.decode_ms_batch(llrs, mi)
+        assert all(np.array_equal(np.asarray(g).astype(np.int64), np.asarray(w).astype(np.int64)) for g, w in zip(got, want)), (code, mi)
+print("OK")
+''' % (root, root, root, codes)
+    out = subprocess.check_output([sys.executable, "-c", script], env=dict(os.environ, LABRADOR_LDPC_NO_REBUILD="1", **env), text=True)
+    assert "OK" in out
