@@ -744,10 +744,12 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
                               size_t batch, size_t max_iters, uint8_t *success, uint32_t *iters, cudaStream_t stream) {
     static const int forced = [] { const char *e = getenv("LABRADOR_LDPC_TM_ARITH"); return e ? atoi(e) : 0; }();
     const int arith = forced ? forced : default_arith;
-    if constexpr (M == 2048) {   // TM8192: 2 words per thread (512 threads x <=128 registers) is also compiled
-        static const int wpt = [] { const char *e = getenv("LABRADOR_LDPC_TM_WPT"); return e ? atoi(e) : 2; }();
+    if constexpr (M == 2048) {   // TM8192: one word slot per thread (1024 threads x 64 registers, default: +1.4 % with the fp16
+                                 // check side, it was -3.2 % with the integer one) or two (512 threads x <= 128 registers:
+                                 // LABRADOR_LDPC_TM_WPT=2, the fused front ends and the cycle profile of LABRADOR_LDPC_TM_PROF)
+        static const bool prof = [] { const char *e = getenv("LABRADOR_LDPC_TM_PROF"); return e && atoi(e) != 0; }();
+        static const int wpt = [] { const char *e = getenv("LABRADOR_LDPC_TM_WPT"); return e ? atoi(e) : (prof ? 2 : 1); }();
         if (wpt == 2) {
-            static const bool prof = [] { const char *e = getenv("LABRADOR_LDPC_TM_PROF"); return e && atoi(e) != 0; }();
             if (prof) {
                 if (arith == 2) return launch_tm<RATE, M, 2, 2, 6, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
                 if (arith == 4) return launch_tm<RATE, M, 2, 4, 0, 1, kFrontNone, true>(ctx, c, l, output, batch, max_iters, success, iters, stream);
