@@ -214,6 +214,9 @@ __device__ __forceinline__ void min_excluding_self(const uint32_t (&a)[kMaxDeg],
 //            v_cor = v keep + 0 (one HFMA2); mu * 2^-24 (one HMUL2) is the integer the variable side adds.
 //            Five FMA-pipe instructions replace IMAD + LOP3 + PRMT + LOP3 + HADD2; signs are bit 15 of the lanes
 //   ARITH 9: ARITH 8 with the sign of u from an fp16 product (HMUL2 of a +-0 word and v_cor) instead of a LOP3
+//   ARITH 11: ARITH 10 with the lane swap of a permuted message done by a PRMT with a per-thread selector instead of a
+//            funnel shift with a per-thread amount: on the way in the same PRMT also writes the 0x64 exponent bytes
+//            (one instruction instead of IMAD + SHF)
 //   ARITH 10: ARITH 8 with u = +-mu by one HFMA2: mu * (+-1.0) + 1536 has the bit pattern 0x6600 +- mu, a per-lane
 //            subtraction leaves the two's-complement message (LOP3 + HFMA2 + VIADD.16x2 instead of
 //            HMUL2 + PRMT + HMUL2 + VIADD.16x2 + LOP3)
@@ -285,7 +288,11 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                 const int borrow = wv < phi_lo ? 1 : 0;
                 const int w = (wv - phi_lo) & (S - 1);
                 paddr[ps][wi] = (uint32_t)(ps * (M / 2) + q * S + w);
-                pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 16u : 0u;
+                // rotation amount of the funnel shift that swaps the lanes -- or, ARITH 11, the selector of the PRMT that does:
+                // bytes (s0, 4 + s0 + 1, s2, 4 + s2 + 1) with (s0, s2) = (0, 2) or (2, 0).  With both operands the same word
+                // that is the lane swap; with 0x64646464 as the second operand it also sets the fp16 exponent of 1024 + C
+                if constexpr (ARITH == 11) pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 0x5072u : 0x7250u;
+                else pswp[ps][wi] = ((phi_hi ^ borrow) & 1) ? 16u : 0u;
             }
         });
     }
@@ -367,7 +374,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
 #pragma unroll
             for (int i = 0; i < NI; i++) idm[i][wi] = 0;
 #pragma unroll
-            for (int b = 0; b < NB; b++) cc[b][wi] = (ARITH >= 8 && ARITH <= 10) ? 0u : 0x007f007fu;
+            for (int b = 0; b < NB; b++) cc[b][wi] = (ARITH >= 8 && ARITH <= 11) ? 0u : 0x007f007fu;
 #pragma unroll
             for (int p = 0; p < NP; p++) msg[p * (M / 2) + wd] = 0;
         }
@@ -436,7 +443,9 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             uint32_t u;
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
-                                u = lane_rot(msg[paddr[ps][wi]], pswp[ps][wi]);
+                                const uint32_t w = msg[paddr[ps][wi]];
+                                if constexpr (ARITH == 11) u = __byte_perm(w, w, pswp[ps][wi]);
+                                else u = lane_rot(w, pswp[ps][wi]);
                             } else {
                                 u = idm[count_i<P>(b)][wi];
                             }
@@ -489,10 +498,13 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             if constexpr (ARITH != 2) cv = __viaddmin_s16x2_relu(van, ub[k], 0x00fe00feu);
                             else cv = pmin<CV_F>(f_relu_add(van, ub[k]), 0x00fe00feu);
                             if constexpr (PIGGY && b == 2) cv = va * c256 + cv;          // high byte: the biased marginal
-                            else if constexpr (ARITH >= 8 && ARITH <= 10) cv = cv * one + 0x64006400u;   // as fp16: 1024 + C
+                            else if constexpr ((ARITH >= 8 && ARITH <= 10) || (ARITH == 11 && !P::blk(b).isp))
+                                cv = cv * one + 0x64006400u;                                 // as fp16: 1024 + C
                             if constexpr (P::blk(b).isp) {
                                 constexpr int ps = count_p<P>(b);
-                                msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
+                                if constexpr (ARITH == 11 && PIGGY && b == 2) msg[paddr[ps][wi]] = __byte_perm(cv, cv, pswp[ps][wi]);
+                                else if constexpr (ARITH == 11) msg[paddr[ps][wi]] = __byte_perm(cv, 0x64646464u, pswp[ps][wi]);   // swap + exponent
+                                else msg[paddr[ps][wi]] = lane_rot(cv, pswp[ps][wi]);
                             } else {
                                 idm[count_i<P>(b)][wi] = cv;
                             }
@@ -523,10 +535,10 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                             if constexpr (PIGGY && b == 2) {
                                 // three marginals of this check: (biased bit 7 of each) XORed = NOT the parity of the hard bits
                                 bad[wi] = ~(hloc8[wi] ^ cv) & 0x80008000u;
-                                if constexpr (ARITH >= 8 && ARITH <= 10) cv = (cv & 0x00ff00ffu) | 0x64006400u;
+                                if constexpr (ARITH >= 8 && ARITH <= 11) cv = (cv & 0x00ff00ffu) | 0x64006400u;
                                 else cv &= 0x00ff00ffu;
                             }
-                            if constexpr (ARITH >= 8 && ARITH <= 10) {
+                            if constexpr (ARITH >= 8 && ARITH <= 11) {
                                 const __half2 d = __hsub2(u2h(0x647f647fu), u2h(cv));      // 1151 - (1024 + C) = v, an integer-valued fp16 (0 -> +0)
                                 const __half2 keep = __hfma2_sat(d, u2h(cc[b][wi]), u2h(0x3c003c00u));   // sat(v v_old + 1): 0 where the sign flipped and v_old != 0
                                 const __half2 dc = __hfma2(d, keep, u2h(0u));              // killed -> +0
@@ -550,9 +562,9 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                         }
                     });
                     if constexpr (ARITH == 9) sx &= 0x80008000u;                          // +-0 in both lanes
-                    if constexpr (ARITH == 10) sx = (sx & 0x80008000u) ^ 0x3c003c00u;     // +-1.0 in both lanes
+                    if constexpr (ARITH >= 10) sx = (sx & 0x80008000u) ^ 0x3c003c00u;     // +-1.0 in both lanes
                     if constexpr (ARITH == 5) min_excluding_self3<DC>(a, mu);
-                    else if constexpr (ARITH >= 6 && ARITH <= 10) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
+                    else if constexpr (ARITH >= 6 && ARITH <= 11) min_excluding_self_h<DC, (KNOBS & 16) != 0>(a, mu);
                     else if constexpr (ARITH == 1 || ARITH == 3) min_excluding_self<DC, false, false, false>(a, mu);
                     else min_excluding_self<DC, SUF_F, PRE_F, COMB_F>(a, mu);
                     static_for<0, NB>([&](auto bi) {
@@ -571,7 +583,7 @@ decode_ms_tm_i8_kernel(const TmParams prm, const typename FrontSrc<FRONT, int8_t
                                 const uint32_t nm = prmt_sign15(sx ^ ck[k]);
                                 const uint32_t mi = h2u(__hmul2(u2h(mu[k]), u2h(0x00010001u)));   // mu * 2^-24: the integer in the low bits
                                 u = __vadd2(mi, nm) ^ nm;
-                            } else if constexpr (ARITH == 10) {
+                            } else if constexpr (ARITH >= 10) {
                                 // +-1.0 with the sign of u; 1536 +- mu has the bits 0x6600 +- mu (ulp 1 in [1024, 2048))
                                 const uint32_t pm = sx ^ (ck[k] & 0x80008000u);
                                 u = __vadd2(h2u(__hfma2(u2h(mu[k]), u2h(pm), u2h(0x66006600u))), 0x9a009a00u);
@@ -763,6 +775,7 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
             if (arith == 832) return launch_tm<RATE, M, 2, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 932) return launch_tm<RATE, M, 2, 9, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 1032) return launch_tm<RATE, M, 2, 10, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+            if (arith == 1132) return launch_tm<RATE, M, 2, 11, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 6) return launch_tm<RATE, M, 2, 6, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 632) return launch_tm<RATE, M, 2, 6, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
             if (arith == 532) return launch_tm<RATE, M, 2, 5, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
@@ -783,8 +796,10 @@ cudaError_t launch_tm_variant(int default_arith, DeviceCtx &ctx, const CodeInfo 
     if (arith == 832) return launch_tm<RATE, M, 1, 8, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 932) return launch_tm<RATE, M, 1, 9, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 1032) return launch_tm<RATE, M, 1, 10, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
+    if (arith == 1132) return launch_tm<RATE, M, 1, 11, 32>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if (arith == 7) return launch_tm<RATE, M, 1, 7, 0>(ctx, c, l, output, batch, max_iters, success, iters, stream);
     if constexpr (RATE == 2 && M == 512) {
+        if (arith == 11322) return launch_tm<RATE, M, 1, 11, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 10322) return launch_tm<RATE, M, 1, 10, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 9322) return launch_tm<RATE, M, 1, 9, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);
         if (arith == 6322) return launch_tm<RATE, M, 1, 6, 32, 2>(ctx, c, l, output, batch, max_iters, success, iters, stream);

@@ -806,9 +806,9 @@ def test_many_async_launches_on_several_streams(ldpc, oracle):
 @pytest.mark.parametrize("env", [{"LABRADOR_LDPC_TC_X2_HABS": "0"}, {"LABRADOR_LDPC_TC_X2_HABS": "1"},
                                  {"LABRADOR_LDPC_TC_X2_HABS": "2"}, {"LABRADOR_LDPC_TC_X2_HABS": "3"},
                                  {"LABRADOR_LDPC_TM_ARITH": "632"}, {"LABRADOR_LDPC_TM_ARITH": "932"},
-                                 {"LABRADOR_LDPC_TM_ARITH": "5"}, {"LABRADOR_LDPC_TM_WPT": "2"}],
+                                 {"LABRADOR_LDPC_TM_ARITH": "5"}, {"LABRADOR_LDPC_TM_ARITH": "1132"}, {"LABRADOR_LDPC_TM_WPT": "2"}],
                          ids=["tc-int", "tc-fp16-minima", "tc-fp16-check-side", "tc-hard-bits-in-messages",
-                              "tm-arith-632", "tm-arith-932", "tm-arith-5", "tm8192-two-slots-per-thread"])
+                              "tm-arith-632", "tm-arith-932", "tm-arith-5", "tm-arith-1132", "tm8192-two-slots-per-thread"])
 def test_i8_min_sum_arithmetic_variants_stay_exact(env):
     """The i8 min-sum kernels keep their earlier arithmetic forms selectable (integer lanes, fp16 only for the minima,
     fp16 check side, hard decisions inside the messages): every one of them must reproduce the oracle bit for bit,
