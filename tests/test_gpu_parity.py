@@ -838,3 +838,25 @@ print("OK")
 ''' % (root, root, root, codes)
     out = subprocess.check_output([sys.executable, "-c", script], env=dict(os.environ, LABRADOR_LDPC_NO_REBUILD="1", **env), text=True)
     assert "OK" in out
+
+
+@pytest.mark.parametrize("code", list(range(9)))
+def test_i8_unstructured_llrs_run_the_whole_iteration_budget(ldpc, oracle, code):
+    """LLRs that are not a noisy codeword at all -- uniform over the whole i8 range, sparse large values among zeros,
+    two-valued +-1, long runs of -128 -- never converge: 100 iterations of saturating additions, sign flips on almost
+    every edge (the self-correction rule fires constantly) and ties in the minima.  Decoded bytes, flags and iteration
+    counts must equal the oracle's."""
+    c = ldpc.LDPCCode(code)
+    n = c.n()
+    rng = np.random.default_rng(4242 + code)
+    rows = [rng.integers(-128, 128, (24, n)),                                   # uniform
+            rng.integers(-128, 128, (8, n)) * (rng.random((8, n)) < 0.1),       # sparse among zeros
+            rng.choice([-1, 1], (8, n)),                                        # smallest magnitudes: ties everywhere
+            rng.choice([-128, -127, 127], (8, n)),                              # the three extreme values
+            np.where(rng.random((8, n)) < 0.5, -128, rng.integers(-3, 4, (8, n)))]
+    llrs = np.concatenate(rows).astype(np.int8)
+    for mi in (100, 7):
+        want = oracle.decode_ms_batch(code, llrs, mi, nthreads=16)
+        got = c.decode_ms_batch(llrs, mi)
+        assert_exact(got, want, "%s unstructured LLRs, maxiters %d" % (c.name if hasattr(c, "name") else code, mi))
+    assert int(np.asarray(want[1]).sum()) < len(llrs)                           # (the cap was really reached)
