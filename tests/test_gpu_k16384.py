@@ -193,3 +193,17 @@ def test_cluster_kernel_variants_match_oracle(ldpc, oracle, env):
             z = np.load(d + "/o.npz")
             assert_exact((z["out"], z["ok"], z["it"]), oracle.decode_ms_batch(code, llrs, 40, nthreads=16),
                          "%s cluster kernel %r" % (CODES[code], env))
+
+
+@pytest.mark.parametrize("code", list(CODES))
+def test_cluster_kernel_unstructured_llrs(ldpc, oracle, code):
+    """LLRs that never converge (uniform over the i8 range, +-1 only, the extreme values): every iteration saturates and
+    the self-correction rule fires on most edges; 30 iterations through the cluster kernel against the oracle."""
+    c = ldpc.LDPCCode(code)
+    n = c.n()
+    rng = np.random.default_rng(5151 + code)
+    llrs = np.concatenate([rng.integers(-128, 128, (6, n)), rng.choice([-1, 1], (3, n)),
+                           rng.choice([-128, -127, 127], (3, n))]).astype(np.int8)
+    for mi in (30, 4):
+        assert_exact(c.decode_ms_batch(llrs, mi), oracle.decode_ms_batch(code, llrs, mi, nthreads=16),
+                     "%s unstructured LLRs, maxiters %d" % (CODES[code], mi))
